@@ -1,0 +1,90 @@
+/*
+ * miphei_b200 — C ABI of the B200-native (sm_100a) kernels behind the MIPHEI-ViT generator hot path.
+ *
+ * The reference (Sanofi-Public/MIPHEI-ViT) has no native layer: every op below replaces a PyTorch/timm library
+ * dispatch on the path  get_generator("myvitmatte") -> ViTMatte.forward  (src/generators/mipheivit.py:106-110)
+ * and its backward / optimiser step (src/models.py:87-139).  Each entry point cites the reference line whose
+ * arithmetic it implements.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MV_ERR_* code or a positive cudaError_t otherwise;
+ *     mv_last_error() returns a human-readable message for the calling thread.  Nothing throws.
+ *   - all pointers are DEVICE pointers owned by the caller (torch tensors in practice); kernels never allocate
+ *     or free; `stream` is a cudaStream_t passed as void*.
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS; "tokens" are [M, C] rows,
+ *     decoder feature maps are NHWC.
+ *   - no CPU fallback exists: without a visible sm_100 device mv_init() fails.
+ */
+#ifndef MIPHEI_B200_H_
+#define MIPHEI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MV_OK 0
+#define MV_ERR_ARG (-1)      /* bad shape / alignment / null pointer */
+#define MV_ERR_DEVICE (-2)   /* no sm_100 device, driver entry point missing */
+#define MV_ERR_LAUNCH (-3)   /* kernel launch failed */
+
+int mv_init(int device);
+const char* mv_last_error(void);
+int mv_version(void);
+int mv_num_sms(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches") */
+int64_t mv_launch_count(void);
+void mv_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM  D = epilogue(A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma),
+ * operands staged by TMA.  Replaces every nn.Linear on the path (timm Attention.qkv / proj, GluMlp.fc1 / fc2 —
+ * created at src/generators/foundation_models.py:53-57; LoRA-extended qkv src/generators/lora.py:29-33), the
+ * patch-embedding conv (timm PatchEmbed.proj) and, through im2col, the decoder 3x3 convs
+ * (src/generators/mipheivit.py:20-41).
+ *
+ *   MV_GEMM_LINEAR     v = acc*scale[n] + shift[n]; v = act(v); v += resid[r(m), n]; out[o(m), n] = v
+ *                      (scale/shift/resid optional; out bf16 or fp32; optional bf16 copy to aux)
+ *                      o(m) = m                                   if rows_per_group == 0
+ *                           = (m / rpg) * group_stride + m % rpg + row_offset   otherwise (patch tokens -> token rows)
+ *                      r(m) = m % rpg if resid_row_mod else o(m)
+ *   MV_GEMM_SWIGLU     B holds [gate rows | value rows] (N = 2*H): out[m, j] = silu(g) * v with
+ *                      g = acc[m, j] + shift[j], v = acc[m, H + j] + shift[H + j]   (timm GluMlp, gate first);
+ *                      aux (optional, bf16 [M, N]) receives the pre-activations [g | v] for the backward pass.
+ *   MV_GEMM_SWIGLU_BWD acc = dU[M, H]; in2 = saved pre-activations [g | v] (bf16 [M, 2H]);
+ *                      out[m, j] = acc * v * silu'(g), out[m, H + j] = acc * silu(g)     (bf16 [M, 2H])
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2 };
+enum { MV_ACT_NONE = 0, MV_ACT_RELU = 1 };
+
+typedef struct mv_gemm_args {
+  const void* a;      /* bf16 [M, K] */
+  int64_t lda;
+  const void* b;      /* bf16 [N, K] */
+  int64_t ldb;
+  int32_t m, n, k;
+  int32_t mode;       /* MV_GEMM_* */
+  int32_t act;        /* MV_ACT_* (LINEAR only) */
+  int32_t out_f32;    /* 1: out is fp32, 0: bf16 */
+  void* out;
+  int64_t ldo;
+  void* aux;          /* optional bf16 second output */
+  int64_t ldaux;
+  const float* scale; /* [N] or NULL */
+  const float* shift; /* [N] or NULL */
+  const float* resid; /* fp32 or NULL */
+  int64_t ldr;
+  const void* in2;    /* bf16, SWIGLU_BWD only */
+  int64_t ldin2;
+  int32_t rows_per_group, group_stride, row_offset, resid_row_mod;
+  int32_t block_n;    /* 0 = choose */
+  int32_t reserved;
+} mv_gemm_args;
+
+int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPHEI_B200_H_ */

@@ -1,0 +1,431 @@
+// bf16 tensor-core GEMM for sm_100a:  D = epilogue(A[M,K] . B[N,K]^T)
+//
+//   * persistent, one CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
+//     warps 2..5 = epilogue (TMEM -> registers -> global)
+//   * operands: TMA 128-byte-swizzled K-major tiles (BLOCK_K = 64 bf16 = 128 B rows), STAGES-deep mbarrier ring
+//   * accumulators: fp32 in TMEM, two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   * M tails: TMA zero-fills out-of-range rows, the epilogue masks the stores; N tails masked per 8 columns
+//
+// Reference ops replaced: every nn.Linear of the timm ViT created at src/generators/foundation_models.py:53-57,
+// QkvWithLoRA (src/generators/lora.py:29-33) through a K-extended weight, and the decoder convs through im2col.
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+
+namespace mv {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmDev {
+  int m, n, k;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int act, out_f32;
+  void* out;
+  long long ldo;
+  void* aux;
+  long long ldaux;
+  const float* scale;
+  const float* shift;
+  const float* resid;
+  long long ldr;
+  const void* in2;
+  long long ldin2;
+  int rows_per_group, group_stride, row_offset, resid_row_mod;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kBoxRowsB = BLOCK_N < 128 ? BLOCK_N : 128;
+  static constexpr int kBoxesB = BLOCK_N / kBoxRowsB;
+  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ epilogue pieces (one thread = one output row)
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float* f) {
+  uint4 u = *reinterpret_cast<const uint4*>(src);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+template <int CH>
+__device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const uint32_t* v, int m, int n) {
+  // v: CH fp32 accumulators for row m, columns n .. n+CH-1
+  long long orow = m, rrow = m;
+  if (p.rows_per_group > 0) {
+    int g = m / p.rows_per_group, r = m - g * p.rows_per_group;
+    orow = (long long)g * p.group_stride + r + p.row_offset;
+    rrow = p.resid_row_mod ? r : orow;
+  }
+#pragma unroll
+  for (int j8 = 0; j8 < CH / 8; ++j8) {
+    const int nn = n + j8 * 8;
+    if (nn >= p.n) break;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+    if (p.scale) {
+      float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
+      float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + nn + 4));
+      f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+      f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+    }
+    if (p.shift) {
+      float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
+      float4 s1 = __ldg(reinterpret_cast<const float4*>(p.shift + nn + 4));
+      f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w;
+      f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
+    }
+    if (p.act == MV_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.resid) {
+      const float* r = p.resid + rrow * p.ldr + nn;
+      float4 r0 = *reinterpret_cast<const float4*>(r);
+      float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+      f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+      f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+    }
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + nn;
+      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      if (p.aux) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.aux) + orow * p.ldaux + nn, f);
+    } else {
+      store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nn, f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmDev p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::kStageBytes + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
+        const int m0 = m_blk * GEMM_BLOCK_M;
+        int brow[2];
+        if (MODE == MV_GEMM_SWIGLU) {  // 128 gate rows + the matching 128 value rows
+          brow[0] = n_blk * 128;
+          brow[1] = p.n / 2 + n_blk * 128;
+        } else {
+          brow[0] = n_blk * BLOCK_N;
+          brow[1] = n_blk * BLOCK_N + 128;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
+#pragma unroll
+          for (int bx = 0; bx < Cfg::kBoxesB; ++bx)
+            tma_load_2d(sb + bx * (Cfg::kBoxRowsB * 128), &tmap_b, full_bar(stage), kb * GEMM_BLOCK_K, brow[bx]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int m = m_blk * GEMM_BLOCK_M + row_in_tile;
+      const bool row_ok = m < p.m;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
+
+      if constexpr (MODE == MV_GEMM_LINEAR) {
+        constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / CH; ++c) {
+          uint32_t v[CH];
+          if constexpr (CH == 32) tmem_ld32(taddr + c * CH, v);
+          else tmem_ld16(taddr + c * CH, v);
+          tmem_ld_wait();
+          if (row_ok) epilogue_linear_chunk<CH>(p, v, m, n_blk * BLOCK_N + c * CH);
+        }
+      } else if constexpr (MODE == MV_GEMM_SWIGLU) {
+        // tile columns [0,128) = gate, [128,256) = value for hidden units n_blk*128 ..
+        const int half = p.n / 2;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(taddr + c * 32, g);
+          tmem_ld32(taddr + 128 + c * 32, u);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int j0 = n_blk * 128 + c * 32;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int jj = j0 + j8 * 8;
+              float fg[8], fv[8], fo[8];
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + jj));
+              float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + jj + 4));
+              float4 c0 = __ldg(reinterpret_cast<const float4*>(p.shift + half + jj));
+              float4 c1 = __ldg(reinterpret_cast<const float4*>(p.shift + half + jj + 4));
+              const float bg[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const float bv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                fg[j] = __uint_as_float(g[j8 * 8 + j]) + bg[j];
+                fv[j] = __uint_as_float(u[j8 * 8 + j]) + bv[j];
+                fo[j] = silu_f(fg[j]) * fv[j];
+              }
+              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo + jj, fo);
+              if (p.aux) {
+                __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)m * p.ldaux;
+                store_bf16x8(h + jj, fg);
+                store_bf16x8(h + half + jj, fv);
+              }
+            }
+          }
+        }
+      } else {  // MV_GEMM_SWIGLU_BWD: acc = dU tile (128 hidden units); N == H
+        const int H = p.n;
+        constexpr int CH = 32;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / CH; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * CH, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int j0 = n_blk * BLOCK_N + c * CH;
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)m * p.ldin2;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int jj = j0 + j8 * 8;
+              if (jj >= H) break;
+              float fg[8], fv[8], dg[8], dv[8];
+              load_bf16x8(h + jj, fg);
+              load_bf16x8(h + H + jj, fv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float du = __uint_as_float(v[j8 * 8 + j]);
+                const float sg = 1.f / (1.f + __expf(-fg[j]));
+                const float sl = fg[j] * sg;
+                dg[j] = du * fv[j] * (sg * (1.f + fg[j] * (1.f - sg)));
+                dv[j] = du * sl;
+              }
+              store_bf16x8(o + jj, dg);
+              store_bf16x8(o + H + jj, dv);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host launch
+template <int BLOCK_N, int MODE>
+static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm<%d,%d>): %s", BLOCK_N, MODE, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const CUtensorMap* ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
+  const CUtensorMap* tb = get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
+  if (!ta || !tb) return MV_ERR_ARG;
+
+  GemmDev p;
+  p.m = a.m; p.n = a.n; p.k = a.k;
+  p.num_m_blocks = (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.num_n_blocks = MODE == MV_GEMM_SWIGLU ? (a.n / 2) / 128 : (a.n + BLOCK_N - 1) / BLOCK_N;
+  p.num_k_blocks = (a.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  p.act = a.act; p.out_f32 = a.out_f32;
+  p.out = a.out; p.ldo = a.ldo; p.aux = a.aux; p.ldaux = a.ldaux;
+  p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.ldr = a.ldr;
+  p.in2 = a.in2; p.ldin2 = a.ldin2;
+  p.rows_per_group = a.rows_per_group; p.group_stride = a.group_stride; p.row_offset = a.row_offset;
+  p.resid_row_mod = a.resid_row_mod;
+
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = device_sms() > 0 ? device_sms() : 148;
+  if (tiles < grid) grid = tiles;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *tb, p);
+  MV_CHECK_LAUNCH("gemm_bf16_tc");
+  return MV_OK;
+}
+
+}  // namespace mv
+
+extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(args != nullptr, "mv_gemm_bf16: null args");
+  const mv_gemm_args& a = *args;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MV_CHECK_ARG(a.a && a.b && a.out, "mv_gemm_bf16: null operand");
+  MV_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0, "mv_gemm_bf16: empty problem m=%d n=%d k=%d", a.m, a.n, a.k);
+  MV_CHECK_ARG(a.n % 8 == 0, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
+  MV_CHECK_ARG(a.k % 8 == 0, "mv_gemm_bf16: K=%d must be a multiple of 8", a.k);
+  MV_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0, "mv_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  MV_CHECK_ARG(a.ldo % (a.out_f32 ? 4 : 8) == 0, "mv_gemm_bf16: ldo alignment");
+  MV_CHECK_ARG((reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "mv_gemm_bf16: out must be 16-byte aligned");
+  MV_CHECK_ARG(!a.resid || ((reinterpret_cast<uintptr_t>(a.resid) & 15) == 0 && a.ldr % 4 == 0), "mv_gemm_bf16: resid alignment");
+  MV_CHECK_ARG(!a.aux || ((reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && a.ldaux % 8 == 0), "mv_gemm_bf16: aux alignment");
+  MV_CHECK_ARG(!a.scale || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0, "mv_gemm_bf16: scale alignment");
+  MV_CHECK_ARG(!a.shift || (reinterpret_cast<uintptr_t>(a.shift) & 15) == 0, "mv_gemm_bf16: shift alignment");
+
+  switch (a.mode) {
+    case MV_GEMM_SWIGLU:
+      MV_CHECK_ARG(a.n % 256 == 0 && a.shift && !a.out_f32, "mv_gemm_bf16(SWIGLU): N %% 256 == 0, bias required, bf16 out");
+      return launch_gemm<256, MV_GEMM_SWIGLU>(a, stream);
+    case MV_GEMM_SWIGLU_BWD:
+      MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
+      return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
+    case MV_GEMM_LINEAR: {
+      int bn = a.block_n;
+      if (bn == 0) {
+        if (a.n <= 16) bn = 16;
+        else if (a.n <= 32) bn = 32;
+        else if (a.n <= 64) bn = 64;
+        else if (a.n <= 128 || a.n % 256 != 0) bn = 128;
+        else {
+          // pick the tile width with the better last-wave occupancy on this problem
+          const int sms = device_sms() > 0 ? device_sms() : 148;
+          const int mb = (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+          auto waves_cost = [&](int b) {
+            const int t = mb * ((a.n + b - 1) / b);
+            return (double)((t + sms - 1) / sms) * b;  // time ~ waves * tile width
+          };
+          bn = waves_cost(256) <= waves_cost(128) * 1.02 ? 256 : 128;
+        }
+      }
+      switch (bn) {
+        case 16: return launch_gemm<16, MV_GEMM_LINEAR>(a, stream);
+        case 32: return launch_gemm<32, MV_GEMM_LINEAR>(a, stream);
+        case 64: return launch_gemm<64, MV_GEMM_LINEAR>(a, stream);
+        case 128: return launch_gemm<128, MV_GEMM_LINEAR>(a, stream);
+        case 256: return launch_gemm<256, MV_GEMM_LINEAR>(a, stream);
+        default: set_error("mv_gemm_bf16: unsupported block_n %d", bn); return MV_ERR_ARG;
+      }
+    }
+    default:
+      set_error("mv_gemm_bf16: unknown mode %d", a.mode);
+      return MV_ERR_ARG;
+  }
+}

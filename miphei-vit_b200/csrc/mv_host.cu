@@ -1,0 +1,165 @@
+// Host plumbing: init, error strings, launch counter, TMA descriptor creation through the driver entry point
+// (resolved at run time with cudaGetDriverEntryPoint so the library does not link libcuda).
+#include "mv_host.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+namespace mv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static int g_sms = 0;
+static int g_device = -1;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int device_sms() { return g_sms; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* ptr, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  if (!g_encode) {
+    set_error("mv_init() has not been called (no TMA encoder)");
+    return MV_ERR_DEVICE;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (uint32_t i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = g_encode(out, dt, rank, ptr, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %u dims %llu,%llu ld %llu box %u,%u ptr %p)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0, ptr);
+    return MV_ERR_ARG;
+  }
+  return MV_OK;
+}
+
+struct TmapKey {
+  const void* p;
+  uint64_t rows, cols, ld;
+  uint32_t br, bc;
+  bool operator==(const TmapKey& o) const {
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && br == o.br && bc == o.bc;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.p) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 1315423911ull + (h << 6) + (h >> 2));
+    h ^= (k.ld * 2654435761ull + (h << 6) + (h >> 2));
+    h ^= ((uint64_t)k.br << 32 | k.bc) + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> g_tmaps;
+
+const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                                    uint32_t box_cols) {
+  TmapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte multiple pitch (ptr %p ld %llu)", ptr,
+              (unsigned long long)ld);
+    return nullptr;
+  }
+  void* mem = nullptr;
+  if (posix_memalign(&mem, 64, sizeof(CUtensorMap)) != 0) {
+    set_error("out of host memory");
+    return nullptr;
+  }
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(mem);
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * 2};
+  uint32_t box[2] = {box_cols, box_rows};
+  if (encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  CU_TENSOR_MAP_SWIZZLE_128B) != MV_OK) {
+    free(mem);
+    return nullptr;
+  }
+  if (g_tmaps.size() > 65536) {  // unbounded growth guard: descriptors are tiny, but pointers may churn
+    for (auto& kv : g_tmaps) free(kv.second);
+    g_tmaps.clear();
+  }
+  g_tmaps.emplace(key, tm);
+  return tm;
+}
+
+}  // namespace mv
+
+extern "C" {
+
+int mv_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    mv::set_error("no CUDA device visible (%s); miphei_b200 has no CPU fallback", cudaGetErrorString(e));
+    return MV_ERR_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    mv::set_error("device %d out of range (%d visible)", device, n);
+    return MV_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    mv::set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  if (prop.major != 10) {
+    mv::set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return MV_ERR_DEVICE;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    mv::set_error("cudaSetDevice: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  mv::g_sms = prop.multiProcessorCount;
+  mv::g_device = device;
+  if (!mv::g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      mv::set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return MV_ERR_DEVICE;
+    }
+    mv::g_encode = reinterpret_cast<mv::EncodeTiledFn>(fn);
+  }
+  return MV_OK;
+}
+
+const char* mv_last_error(void) { return mv::g_err; }
+int mv_version(void) { return 100; }
+int mv_num_sms(void) { return mv::g_sms; }
+int64_t mv_launch_count(void) { return mv::g_launches.load(); }
+void mv_reset_launch_count(void) { mv::g_launches.store(0); }
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Host-side plumbing shared by all translation units: error reporting, launch accounting, TMA descriptor cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/miphei_b200.h"
+
+namespace mv {
+
+void set_error(const char* fmt, ...);
+int device_sms();
+void count_launch(int n = 1);
+
+// 2-D bf16 row-major tensor map: inner extent `cols` (elements), outer extent `rows`, row pitch `ld` elements.
+// Box = box_cols x box_rows, 128-byte swizzle (box_cols * 2 bytes must be 128), OOB reads return zeros.
+// Cached by (ptr, rows, cols, ld, box); returns nullptr and sets the error string on failure.
+const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                                    uint32_t box_cols = 64);
+// Generic encoder (rank <= 5) for kernels that need other layouts; not cached.
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* ptr, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+#define MV_CHECK_ARG(cond, ...)       \
+  do {                                \
+    if (!(cond)) {                    \
+      mv::set_error(__VA_ARGS__);     \
+      return MV_ERR_ARG;              \
+    }                                 \
+  } while (0)
+
+#define MV_CHECK_LAUNCH(name)                                                   \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      mv::set_error("%s launch failed: %s", name, cudaGetErrorString(e__));     \
+      return (int)e__;                                                          \
+    }                                                                           \
+    mv::count_launch();                                                         \
+  } while (0)
+
+}  // namespace mv

@@ -1,0 +1,77 @@
+"""Tensor-level wrappers over the C ABI: they take torch CUDA tensors, pass raw pointers / strides / the current
+stream to libmiphei_b200.so and return torch tensors.  No arithmetic happens in Python or in torch here."""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD = 0, 1, 2
+ACT_NONE, ACT_RELU = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _lib_for(t):
+    if not t.is_cuda:
+        raise _lib.MipheiB200Error("miphei_b200 ops need CUDA tensors (got %s); there is no CPU path" % t.device)
+    return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _rowmajor(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("%s must be 2-D with unit inner stride, got shape %s stride %s" % (name, tuple(t.shape), t.stride()))
+    return t
+
+
+def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
+         resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
+         resid_row_mod=False, block_n=0):
+    """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
+    lib = _lib_for(a)
+    _rowmajor(a, "a"), _rowmajor(b, "b")
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    if mode == GEMM_SWIGLU:
+        out_cols = N // 2
+    elif mode == GEMM_SWIGLU_BWD:
+        out_cols = 2 * N
+    else:
+        out_cols = N
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, out_cols), dtype=out_dtype, device=a.device)
+    _rowmajor(out, "out")
+    args = _lib.GemmArgs()
+    args.a, args.lda = a.data_ptr(), a.stride(0)
+    args.b, args.ldb = b.data_ptr(), b.stride(0)
+    args.m, args.n, args.k = M, N, K
+    args.mode, args.act = mode, act
+    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    if aux is not None:
+        args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.is_contiguous()
+        args.scale = scale.data_ptr()
+    if shift is not None:
+        assert shift.dtype == torch.float32 and shift.is_contiguous()
+        args.shift = shift.data_ptr()
+    if resid is not None:
+        assert resid.dtype == torch.float32
+        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+    if in2 is not None:
+        assert in2.dtype == torch.bfloat16
+        args.in2, args.ldin2 = in2.data_ptr(), in2.stride(0)
+    args.rows_per_group, args.group_stride, args.row_offset = rows_per_group, group_stride, row_offset
+    args.resid_row_mod = 1 if resid_row_mod else 0
+    args.block_n = block_n
+    _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")
+    return out

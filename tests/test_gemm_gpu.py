@@ -1,0 +1,114 @@
+"""GPU parity of the tcgen05 GEMM (mv_gemm_bf16) against a plain torch fp32 reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from miphei_vit_b200 import ops
+    return ops
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale)
+
+
+def _close(got, ref, tol):
+    got = got.float()
+    err = (got - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-12
+    assert err / den < tol, "max abs err %g (ref max %g, rel %g)" % (err, den, err / den)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 256, 256), (128, 128, 64, 128),
+    (5264, 4608, 1536, 0), (5264, 1536, 1536, 0), (5264, 1536, 4096, 0), (329, 1536, 1536, 128),
+    (1000, 48, 64, 0), (777, 96, 448, 0), (640, 192, 896, 0), (300, 32, 640, 0), (300, 16, 1536, 0),
+    (2000, 64, 1600, 0), (129, 256, 1600, 256),
+])
+def test_gemm_plain(M, N, K, bn):
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    b = _rand((N, K), 0.05, 2).bfloat16()
+    out = ops.gemm(a, b, block_n=bn)
+    ref = a.float() @ b.float().t()
+    _close(out, ref, 1e-2)
+    outf = ops.gemm(a, b, block_n=bn, out_dtype=torch.float32)
+    _close(outf, ref, 2e-5)
+
+
+def test_gemm_epilogue_linear():
+    ops = _ops()
+    M, N, K = 700, 1536, 512
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    b = _rand((N, K), 0.05, 2).bfloat16()
+    scale = _rand((N,), 1.0, 3)
+    shift = _rand((N,), 1.0, 4)
+    resid = _rand((M, N), 1.0, 5)
+    aux = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, b, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, aux=aux)
+    ref = (a.float() @ b.float().t()) * scale + shift + resid
+    _close(out, ref, 2e-5)
+    _close(aux, ref, 1e-2)
+    out2 = ops.gemm(a, b, scale=scale, shift=shift, act=ops.ACT_RELU)
+    _close(out2, torch.relu((a.float() @ b.float().t()) * scale + shift), 1e-2)
+    # in-place residual update (out aliases resid)
+    r2 = resid.clone()
+    ops.gemm(a, b, shift=shift, resid=r2, out=r2)
+    _close(r2, (a.float() @ b.float().t()) + shift + resid, 2e-5)
+
+
+def test_gemm_row_remap():
+    """patch-embedding form: rows regrouped into token rows with a per-group offset, residual indexed modulo."""
+    ops = _ops()
+    B, P, N, K = 3, 324, 1536, 640
+    a = _rand((B * P, K), 1.0, 1).bfloat16()
+    b = _rand((N, K), 0.05, 2).bfloat16()
+    shift = _rand((N,), 1.0, 4)
+    pos = _rand((P, N), 1.0, 5)
+    out = torch.full((B * 329, N), 7.0, dtype=torch.float32, device="cuda")
+    ops.gemm(a, b, shift=shift, resid=pos, out=out, rows_per_group=P, group_stride=329, row_offset=5, resid_row_mod=True)
+    ref = ((a.float() @ b.float().t()) + shift).view(B, P, N) + pos
+    got = out.view(B, 329, N)
+    _close(got[:, 5:], ref, 2e-5)
+    assert (got[:, :5] == 7.0).all()
+
+
+def test_gemm_swiglu_fwd_bwd():
+    ops = _ops()
+    M, H, K = 600, 4096, 1536
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    w = _rand((2 * H, K), 0.03, 2).bfloat16()
+    bias = _rand((2 * H,), 0.5, 3)
+    h = torch.zeros((M, 2 * H), dtype=torch.bfloat16, device="cuda")
+    u = ops.gemm(a, w, mode=ops.GEMM_SWIGLU, shift=bias, aux=h)
+    pre = a.float() @ w.float().t() + bias
+    ref = torch.nn.functional.silu(pre[:, :H]) * pre[:, H:]
+    _close(u, ref, 1e-2)
+    _close(h, pre, 1e-2)
+    # backward epilogue: dH from dU = dY @ W2 with saved pre-activations
+    dy = _rand((M, 1536), 1.0, 6).bfloat16()
+    w2t = _rand((H, 1536), 0.03, 7).bfloat16()
+    dh = ops.gemm(dy, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=h)
+    du = dy.float() @ w2t.float().t()
+    hg, hv = h.float()[:, :H], h.float()[:, H:]
+    sg = torch.sigmoid(hg)
+    ref_dg = du * hv * (sg * (1 + hg * (1 - sg)))
+    ref_dv = du * hg * sg
+    _close(dh[:, :H], ref_dg, 1e-2)
+    _close(dh[:, H:], ref_dv, 1e-2)
+
+
+def test_gemm_strided_operands():
+    ops = _ops()
+    M, N, K = 500, 256, 1536
+    abuf = _rand((M, 1600), 1.0, 1).bfloat16()
+    b = _rand((N, 1600), 0.05, 2).bfloat16()
+    out = ops.gemm(abuf[:, :K], b[:, :K])
+    _close(out, abuf[:, :K].float() @ b[:, :K].float().t(), 1e-2)
+    obuf = torch.zeros((M, 512), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(abuf, b, out=obuf[:, 256:])
+    _close(obuf[:, 256:], abuf.float() @ b.float().t(), 1e-2)
+    assert (obuf[:, :256] == 0).all()
