@@ -84,6 +84,26 @@ typedef struct mv_gemm_args {
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * LayerNorm over channels of token rows (timm Block.norm1/norm2, final norm; eps 1e-6).
+ *   fwd: x fp32 [M, D] -> y bf16 [M, ldy]; mean/rstd (fp32 [M]) optional, both or neither.
+ *   bwd: dx[M, D] = dres + dLN(x, w)(dy); dy bf16 or fp32; dres optional; optional bf16 copy of dx.
+ *        The affine parameters are frozen on this path (apply_lora, src/generators/lora.py:66-68): no dw / db.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, float* mean,
+                     float* rstd, int m, int d, float eps, void* stream);
+int mv_layernorm_bwd(const float* x, int64_t ldx, const float* w, const void* dy, int64_t lddy, int dy_f32,
+                     const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, int m,
+                     int d, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Self-attention forward, head_dim 64, 16 <= n_tok <= 448 (timm Attention.forward -> F.scaled_dot_product_attention).
+ *   qkv bf16 [batch*n_tok, 3*heads*64] (q | k | v per token, as nn.Linear(dim, 3*dim) lays them out),
+ *   out bf16 [batch*n_tok, heads*64] token-major, lse fp32 [batch, heads, n_tok] (natural log; optional).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, float* lse, int batch, int n_tok, int heads,
+                float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

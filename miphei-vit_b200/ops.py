@@ -75,3 +75,48 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     args.block_n = block_n
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")
     return out
+
+
+def layernorm_fwd(x, w, b, *, out=None, eps=1e-6, stats=False):
+    """y = LayerNorm(x) (mv_layernorm_fwd): x fp32 [M, D] -> bf16 [M, D] (out may be a wider, strided buffer)."""
+    lib = _lib_for(x)
+    _rowmajor(x, "x")
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and b.dtype == torch.float32
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if stats:
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    _lib.check(lib.mv_layernorm_fwd(_ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(out), out.stride(0), _ptr(mean),
+                                    _ptr(rstd), M, D, eps, _stream()), "mv_layernorm_fwd")
+    return (out, mean, rstd) if stats else out
+
+
+def layernorm_bwd(x, w, dy, *, dres=None, eps=1e-6, want_bf16=False):
+    """dx = dres + dLN(dy) (mv_layernorm_bwd); returns fp32 dx (and a bf16 copy when want_bf16)."""
+    lib = _lib_for(x)
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
+    dxb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _lib.check(lib.mv_layernorm_bwd(_ptr(x), x.stride(0), _ptr(w), _ptr(dy), dy.stride(0),
+                                    1 if dy.dtype == torch.float32 else 0, _ptr(dres),
+                                    dres.stride(0) if dres is not None else 0, _ptr(dx), dx.stride(0), _ptr(dxb),
+                                    dxb.stride(0) if dxb is not None else 0, M, D, eps, _stream()), "mv_layernorm_bwd")
+    return (dx, dxb) if want_bf16 else dx
+
+
+def attn_fwd(qkv, batch, n_tok, heads, *, out=None, want_lse=False, scale=None):
+    """softmax(q k^T * scale) v per (image, head) from fused qkv rows (mv_attn_fwd)."""
+    lib = _lib_for(qkv)
+    _rowmajor(qkv, "qkv")
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (batch * n_tok, 3 * heads * 64)
+    if out is None:
+        out = torch.empty((batch * n_tok, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((batch, heads, n_tok), dtype=torch.float32, device=qkv.device) if want_lse else None
+    if scale is None:
+        scale = 64 ** -0.5
+    _lib.check(lib.mv_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), _ptr(lse), batch, n_tok, heads,
+                               float(scale), _stream()), "mv_attn_fwd")
+    return (out, lse) if want_lse else out
