@@ -54,8 +54,24 @@ void mv_reset_launch_count(void);
  *                      aux (optional, bf16 [M, N]) receives the pre-activations [g | v] for the backward pass.
  *   MV_GEMM_SWIGLU_BWD acc = dU[M, H]; in2 = saved pre-activations [g | v] (bf16 [M, 2H]);
  *                      out[m, j] = acc * v * silu'(g), out[m, H + j] = acc * silu(g)     (bf16 [M, 2H])
+ *   MV_GEMM_HEAD_GATE  the attention gate of all SegmentationHeads at once (AttentionBlock.psi, src/generators/
+ *                      unet.py:407-422): B = the heads' 1x1 convs stacked [16*heads, C]; per head h
+ *                      out[m, h] = sigmoid(b2[h] + sum_j w2[16h+j] * relu(acc[m,16h+j]*scale[16h+j] + shift[16h+j]))
+ *                      with w2 = in2 (fp32 [16*heads]), b2 = resid (fp32 [heads]); out bf16 [M, heads].
+ *   MV_GEMM_HEAD_CONV  the gated 3x3 output conv + tanh of all SegmentationHeads at once (unet.py:425-438 looped at
+ *                      mipheivit.py:213-218): conv = 1 over the C<=64 feature map, B = [heads<=16, 9*64] (per tap the
+ *                      head's 3x3 weights over channels); out[b, h, y, x] = tanh(shift[h] + sum_tap g[b, y', x', h] *
+ *                      sum_c B[h, tap, c] f[b, y', x', c]) with g = in2 (bf16 [M, ldin2], the HEAD_GATE output).
+ *                      out is NCHW: out_f32 = 1 fp32, 0 bf16, 2 uint8 through the inference sink mapping
+ *                      ((p+0.9)/1.8).clamp(0,1)*255 truncated (src/callbacks.py:345-346).
+ *
+ * Implicit-GEMM 3x3 convolution (pad 1, stride 1|2; Basic_Conv3x3, src/generators/mipheivit.py:20-41): set conv = 1.
+ * A is then read from one or two NHWC bf16 feature maps (channel concat: a = [B,Hin,Win,c0], a2 = [B,Hin,Win,c1],
+ * Hin = conv_h*stride) as TMA 4-D tiles whose out-of-bounds zero fill is the padding; rows of D are output pixels
+ * (NHWC), M = batch*conv_h*conv_w, and B is [N, 9 * 64 * (ceil(c0/64)+ceil(c1/64))]: per tap (ky,kx) the source-0
+ * channels zero-padded to a multiple of 64, then the source-1 channels likewise.
  * ---------------------------------------------------------------------------------------------------------- */
-enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2 };
+enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2, MV_GEMM_HEAD_GATE = 3, MV_GEMM_HEAD_CONV = 4 };
 enum { MV_ACT_NONE = 0, MV_ACT_RELU = 1 };
 
 typedef struct mv_gemm_args {
@@ -79,7 +95,10 @@ typedef struct mv_gemm_args {
   int64_t ldin2;
   int32_t rows_per_group, group_stride, row_offset, resid_row_mod;
   int32_t block_n;    /* 0 = choose */
-  int32_t reserved;
+  int32_t conv;       /* 1: implicit 3x3 convolution, see above */
+  const void* a2;     /* second NHWC source (channel concat) or NULL */
+  int32_t conv_batch, conv_h, conv_w, conv_stride; /* OUTPUT height/width */
+  int32_t conv_c0, conv_c1;
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
@@ -103,6 +122,22 @@ int mv_layernorm_bwd(const float* x, int64_t ldx, const float* w, const void* dy
  * ---------------------------------------------------------------------------------------------------------- */
 int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, float* lse, int batch, int n_tok, int heads,
                 float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Memory-bound glue of the forward pass.
+ *   mv_prep_input     x fp32 NCHW [B,3,S,S] -> img_nhwc8 bf16 [B,S,S,8] (channels 3..7 zero; D0 of ConvStream,
+ *                     src/generators/mipheivit.py:66-73) and/or patch_matrix bf16 [B*(S/14)^2, 592]: timm
+ *                     PatchEmbed's conv(k14, s14) as a GEMM operand, K = (c, ky, kx) = 588 zero-padded to 592.
+ *   mv_fill_prefix    residual-stream rows of cls + register tokens (timm _pos_embed, no_embed_class=True).
+ *   mv_tokens_to_map  Encoder.forward tail (mipheivit.py:158-162): prefix tokens dropped, g x g token map
+ *                     bicubic-resized (A=-0.75, align_corners False, scale factor target/grid) -> NHWC bf16.
+ *   mv_upsample2x     Fusion_Block's bilinear x2 (mipheivit.py:89), NHWC bf16.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk, void* stream);
+int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int batch, int n_tok, int n_prefix, int dim, void* stream);
+int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid, int target,
+                     int dim, void* stream);
+int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, void* stream);
 
 #ifdef __cplusplus
 }

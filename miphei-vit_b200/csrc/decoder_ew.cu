@@ -1,0 +1,213 @@
+// Memory-bound glue kernels around the GEMMs (all HBM-bound: coalesced, 16-byte vectors where the layout allows).
+//
+//   mv_prep_input        x fp32 NCHW [B,3,S,S] -> NHWC bf16 image padded to 8 channels (D0 of ConvStream,
+//                        mipheivit.py:66-73) and the patch matrix [B*g*g, 592] of timm PatchEmbed (conv k14 s14 as a
+//                        GEMM: K = (c, ky, kx) = 588, zero-padded to 592 for 16-byte rows)
+//   mv_tokens_to_map     Encoder.forward tail, mipheivit.py:158-162: drop the prefix tokens, view as a g x g map,
+//                        F.interpolate(scale_factor=(t/g, t/g), mode="bicubic") -> NHWC bf16 [B,t,t,D]
+//   mv_upsample2x        Fusion_Block's F.interpolate(scale_factor=2, bilinear, align_corners=False), NHWC bf16
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+
+namespace mv {
+
+__global__ void prep_image_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ img, int B, int S) {
+  const long long npix = (long long)B * S * S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long plane = (long long)S * S;
+  const long long b = i / plane, r = i - b * plane;
+  const float* xb = x + b * 3 * plane + r;
+  uint4 o;
+  o.x = pack_bf16x2(xb[0], xb[plane]);
+  o.y = pack_bf16x2(xb[2 * plane], 0.f);
+  o.z = 0u;
+  o.w = 0u;
+  reinterpret_cast<uint4*>(img)[i] = o;
+}
+
+__global__ void patch_matrix_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int S, int g,
+                                    int ldk) {
+  // one thread per (patch row, 8-wide k group); ldk = 592
+  const int groups = ldk / 8;
+  const long long total = (long long)B * g * g * groups;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kg = (int)(i % groups);
+  const long long row = i / groups;
+  const int px = (int)(row % g), py = (int)((row / g) % g);
+  const long long b = row / ((long long)g * g);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg * 8 + j;
+    if (k < 588) {
+      const int c = k / 196, rr = k - c * 196, ky = rr / 14, kx = rr - ky * 14;
+      f[j] = x[((b * 3 + c) * S + (py * 14 + ky)) * (long long)S + px * 14 + kx];
+    } else {
+      f[j] = 0.f;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  reinterpret_cast<uint4*>(a + row * ldk)[kg] = o;
+}
+
+// PyTorch upsample_bicubic2d coefficients (A = -0.75), align_corners = False, explicit scale factor
+__device__ __forceinline__ void cubic_coeffs(float t, float* w) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+// tokens bf16 [B, ntok, ldt] (prefix tokens first) -> out NHWC bf16 [B, t, t, D]; one block per output pixel
+__global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long long ldt, int ntok, int prefix, int g,
+                                     int t, int D, float inv_scale, __nv_bfloat16* __restrict__ out) {
+  const int ox = blockIdx.x % t, oy = (blockIdx.x / t) % t, b = blockIdx.x / (t * t);
+  const float sy = (oy + 0.5f) * inv_scale - 0.5f, sx = (ox + 0.5f) * inv_scale - 0.5f;
+  const int iy = (int)floorf(sy), ix = (int)floorf(sx);
+  float wy[4], wx[4];
+  cubic_coeffs(sy - iy, wy);
+  cubic_coeffs(sx - ix, wx);
+  const __nv_bfloat16* base = tok + ((long long)b * ntok + prefix) * ldt;
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), g - 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int xx = min(max(ix - 1 + e, 0), g - 1);
+        const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)(yy * g + xx) * ldt + c);
+        const float w = wy[a] * wx[e];
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p1.x; acc[3] += w * p1.y;
+        acc[4] += w * p2.x; acc[5] += w * p2.y; acc[6] += w * p3.x; acc[7] += w * p3.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + (((long long)b * t + oy) * t + ox) * D + c) = o;
+  }
+}
+
+// NHWC bf16 [B,h,w,C] -> [B,2h,2w,C], bilinear, align_corners = False; one thread per (output pixel, 8 channels)
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h,
+                                  int w, int C) {
+  const int cg = C / 8;
+  const long long total = (long long)B * 4 * h * w * cg;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cg);
+  long long r = i / cg;
+  const int ox = (int)(r % (2 * w));
+  r /= (2 * w);
+  const int oy = (int)(r % (2 * h));
+  const long long b = r / (2 * h);
+  const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const __nv_bfloat16* ib = in + b * (long long)h * w * C + c8 * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(ib + ((long long)y0 * w + x0) * C);
+  const uint4 bq = *reinterpret_cast<const uint4*>(ib + ((long long)y0 * w + x1) * C);
+  const uint4 c = *reinterpret_cast<const uint4*>(ib + ((long long)y1 * w + x0) * C);
+  const uint4 d = *reinterpret_cast<const uint4*>(ib + ((long long)y1 * w + x1) * C);
+  const uint32_t* pa = &a.x; const uint32_t* pb = &bq.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = unpack_bf16x2(pa[j]), fb = unpack_bf16x2(pb[j]), fc = unpack_bf16x2(pc[j]), fd = unpack_bf16x2(pd[j]);
+    o[j] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                       w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// residual stream rows of the prefix tokens: x[b, j, :] = prefix[j, :] (cls + register tokens, no pos-embed:
+// timm _pos_embed with no_embed_class=True)
+__global__ void fill_prefix_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ prefix, int B, int ntok,
+                                   int nprefix, int D) {
+  const int d4 = D / 4;
+  const long long total = (long long)B * nprefix * d4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % d4);
+  const int j = (int)((i / d4) % nprefix);
+  const long long b = i / ((long long)d4 * nprefix);
+  reinterpret_cast<float4*>(x + (b * ntok + j) * ldx)[c] = reinterpret_cast<const float4*>(prefix + (long long)j * D)[c];
+}
+
+}  // namespace mv
+
+extern "C" int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int batch, int n_tok, int n_prefix, int dim,
+                              void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(x && prefix && batch > 0 && dim % 4 == 0 && ldx % 4 == 0, "mv_fill_prefix: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = (long long)batch * n_prefix * (dim / 4);
+  fill_prefix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, ldx, prefix, batch, n_tok, n_prefix, dim);
+  MV_CHECK_LAUNCH("fill_prefix");
+  return MV_OK;
+}
+
+extern "C" int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
+                             void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(x && batch > 0 && size >= 14, "mv_prep_input: null/empty");
+  MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input: patch matrix pitch must be 592");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (img_nhwc8) {
+    const long long npix = (long long)batch * size * size;
+    prep_image_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(img_nhwc8),
+                                                                          batch, size);
+    MV_CHECK_LAUNCH("prep_image");
+  }
+  if (patch_matrix) {
+    const int g = size / 14;
+    const long long total = (long long)batch * g * g * (ldk / 8);
+    patch_matrix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(patch_matrix), batch, size, g, ldk);
+    MV_CHECK_LAUNCH("patch_matrix");
+  }
+  return MV_OK;
+}
+
+extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid,
+                                int target, int dim, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(tokens && out && batch > 0, "mv_tokens_to_map: null/empty");
+  MV_CHECK_ARG(n_tok == prefix + grid * grid && dim % 8 == 0 && ldt % 8 == 0, "mv_tokens_to_map: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // PyTorch uses the reciprocal of the user-supplied scale factor (target/grid) for the source coordinates
+  const float inv_scale = (float)(1.0 / ((double)target / (double)grid));
+  const int threads = dim / 8 < 256 ? (dim / 8 + 31) / 32 * 32 : 256;
+  tokens_to_map_kernel<<<batch * target * target, threads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
+      reinterpret_cast<__nv_bfloat16*>(out));
+  MV_CHECK_LAUNCH("tokens_to_map");
+  return MV_OK;
+}
+
+extern "C" int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(in && out && batch > 0 && h > 0 && w > 0 && c % 8 == 0, "mv_upsample2x: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = (long long)batch * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
+  MV_CHECK_LAUNCH("upsample2x");
+  return MV_OK;
+}

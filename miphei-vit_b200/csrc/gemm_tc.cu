@@ -32,9 +32,15 @@ struct GemmDev {
   const void* in2;
   long long ldin2;
   int rows_per_group, group_stride, row_offset, resid_row_mod;
+  // implicit-GEMM 3x3 convolution (pad 1) over NHWC sources: A tiles are TMA 4-D boxes, OOB zero fill = padding
+  int conv;            // 0: A is a plain [M, K] matrix
+  int conv_h, conv_w;  // OUTPUT spatial size
+  int conv_tw;         // tile = conv_tw x (128 / conv_tw) output pixels (full rows when conv_w < 128)
+  int conv_stride;     // 1 or 2
+  int conv_cb0, conv_cb1;  // 64-channel blocks per tap taken from source 0 / source 1 (channel concat)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE = 0>
 struct GemmCfg {
   static constexpr int kBoxRowsB = BLOCK_N < 128 ? BLOCK_N : 128;
   static constexpr int kBoxesB = BLOCK_N / kBoxRowsB;
@@ -42,7 +48,9 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
+  static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
+  static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
@@ -118,9 +126,9 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 // ------------------------------------------------------------------ kernel
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmDev p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -139,6 +147,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_a2);
     tma_prefetch_desc(&tmap_b);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
@@ -181,11 +190,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           brow[0] = n_blk * BLOCK_N;
           brow[1] = n_blk * BLOCK_N + 128;
         }
+        int cv_b = 0, cv_y = 0, cv_x = 0;
+        if (p.conv) {  // tile rows are contiguous output pixels: m0 -> (image, y0, x0)
+          const int hw = p.conv_h * p.conv_w;
+          cv_b = m0 / hw;
+          const int rem = m0 - cv_b * hw;
+          cv_y = rem / p.conv_w;
+          cv_x = rem - cv_y * p.conv_w;
+        }
+        const int cbt = p.conv_cb0 + p.conv_cb1;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (p.conv) {
+            const int tap = kb / cbt;
+            const int cbi = kb - tap * cbt;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int ix = cv_x * p.conv_stride + kx - 1;
+            const int iy = cv_y * p.conv_stride + ky - 1;
+            if (cbi < p.conv_cb0) tma_load_4d(sa, &tmap_a, full_bar(stage), cbi * 64, ix, iy, cv_b);
+            else tma_load_4d(sa, &tmap_a2, full_bar(stage), (cbi - p.conv_cb0) * 64, ix, iy, cv_b);
+          } else
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
 #pragma unroll
           for (int bx = 0; bx < Cfg::kBoxesB; ++bx)
@@ -205,7 +232,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -216,7 +243,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (MODE == MV_GEMM_HEAD_CONV) umma_bf16(d_tmem + kb * 16, da + 2 * k, db + 2 * k, idesc, k != 0);
+            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -238,7 +266,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const bool row_ok = m < p.m;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
 
       if constexpr (MODE == MV_GEMM_LINEAR) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
@@ -283,6 +311,71 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 store_bf16x8(h + jj, fg);
                 store_bf16x8(h + half + jj, fv);
               }
+            }
+          }
+        }
+      } else if constexpr (MODE == MV_GEMM_HEAD_GATE) {
+        // columns = heads x 16 hidden units of AttentionBlock.psi: g_h = sigmoid(w2_h . relu(scale*acc+shift) + b2_h)
+        const int heads = p.n / 16;
+        const float* w2 = reinterpret_cast<const float*>(p.in2);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
+#pragma unroll 1
+        for (int hd = 0; hd < heads; ++hd) {
+          uint32_t v[16];
+          tmem_ld16(taddr + hd * 16, v);
+          tmem_ld_wait();
+          float acc = __ldg(p.resid + hd);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = hd * 16 + j;
+            const float a = fmaxf(__uint_as_float(v[j]) * __ldg(p.scale + n) + __ldg(p.shift + n), 0.f);
+            acc += a * __ldg(w2 + n);
+          }
+          if (row_ok) o[hd] = __float2bfloat16(1.f / (1.f + __expf(-acc)));
+        }
+      } else if constexpr (MODE == MV_GEMM_HEAD_CONV) {
+        // columns [16*tap, 16*tap+16): t[h] = sum_c W3[h, c, tap] * f[c](pixel + tap); the 3x3 conv acts on f * g_h,
+        // so each tap is weighted by the gate of the NEIGHBOUR pixel before the taps are summed, then bias + tanh.
+        const int hw = p.conv_h * p.conv_w;
+        const int bimg = m / hw;
+        const int rem = m - bimg * hw;
+        const int py = rem / p.conv_w, px = rem - py * p.conv_w;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t v[16];
+          tmem_ld16(taddr + tap * 16, v);
+          tmem_ld_wait();
+          const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+          if (yy >= 0 && yy < p.conv_h && xx >= 0 && xx < p.conv_w) {
+            const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.in2) + ((long long)bimg * hw + (long long)yy * p.conv_w + xx) * p.ldin2;
+            if (p.ldin2 == 16) {
+              float g[16];
+              load_bf16x8(gp, g);
+              load_bf16x8(gp + 8, g + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] += g[j] * __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < p.n) acc[j] += __bfloat162float(gp[j]) * __uint_as_float(v[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < p.n) {
+            const float z = acc[j] + __ldg(p.shift + j);
+            const float e = __expf(2.f * z);
+            const float t = 1.f - 2.f / (e + 1.f);  // tanh
+            const long long oi = ((long long)bimg * p.n + j) * hw + rem;  // NCHW
+            if (p.out_f32 == 1) reinterpret_cast<float*>(p.out)[oi] = t;
+            else if (p.out_f32 == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[oi] = __float2bfloat16(t);
+            else {  // uint8 sink of SavePredictionsCallback (src/callbacks.py:345-346): truncating conversion
+              const float q = fminf(fmaxf((t + 0.9f) / 1.8f, 0.f), 1.f) * 255.f;
+              reinterpret_cast<uint8_t*>(p.out)[oi] = static_cast<uint8_t>(q);
             }
           }
         }
@@ -336,7 +429,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ------------------------------------------------------------------ host launch
 template <int BLOCK_N, int MODE>
 static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE>;
   if (!attr_set) {
@@ -347,9 +440,22 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const CUtensorMap* ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
+  const CUtensorMap* ta = nullptr;
+  const CUtensorMap* ta2 = nullptr;
+  if (a.conv) {
+    const int tw = a.conv_w < 128 ? a.conv_w : 128;
+    const int th = 128 / tw;
+    ta = get_tmap_nhwc_bf16(a.a, a.conv_batch, a.conv_h * a.conv_stride, a.conv_w * a.conv_stride, a.conv_c0, tw, th,
+                            a.conv_stride);
+    ta2 = a.conv_c1 > 0 ? get_tmap_nhwc_bf16(a.a2, a.conv_batch, a.conv_h * a.conv_stride, a.conv_w * a.conv_stride,
+                                             a.conv_c1, tw, th, a.conv_stride)
+                        : ta;
+  } else {
+    ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
+    ta2 = ta;
+  }
   const CUtensorMap* tb = get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
-  if (!ta || !tb) return MV_ERR_ARG;
+  if (!ta || !ta2 || !tb) return MV_ERR_ARG;
 
   GemmDev p;
   p.m = a.m; p.n = a.n; p.k = a.k;
@@ -362,11 +468,17 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.in2 = a.in2; p.ldin2 = a.ldin2;
   p.rows_per_group = a.rows_per_group; p.group_stride = a.group_stride; p.row_offset = a.row_offset;
   p.resid_row_mod = a.resid_row_mod;
+  p.conv = a.conv;
+  p.conv_h = a.conv_h; p.conv_w = a.conv_w;
+  p.conv_tw = a.conv_w < 128 ? a.conv_w : 128;
+  p.conv_stride = a.conv_stride;
+  p.conv_cb0 = (a.conv_c0 + 63) / 64;
+  p.conv_cb1 = (a.conv_c1 + 63) / 64;
 
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   int grid = device_sms() > 0 ? device_sms() : 148;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
 }
@@ -380,10 +492,24 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MV_CHECK_ARG(a.a && a.b && a.out, "mv_gemm_bf16: null operand");
   MV_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0, "mv_gemm_bf16: empty problem m=%d n=%d k=%d", a.m, a.n, a.k);
-  MV_CHECK_ARG(a.n % 8 == 0, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
+  MV_CHECK_ARG(a.n % 8 == 0 || a.mode == MV_GEMM_HEAD_CONV, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
   MV_CHECK_ARG(a.k % 8 == 0, "mv_gemm_bf16: K=%d must be a multiple of 8", a.k);
-  MV_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0, "mv_gemm_bf16: lda/ldb must be multiples of 8 elements");
-  MV_CHECK_ARG(a.ldo % (a.out_f32 ? 4 : 8) == 0, "mv_gemm_bf16: ldo alignment");
+  MV_CHECK_ARG((a.conv || a.lda % 8 == 0) && a.ldb % 8 == 0, "mv_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  if (a.conv) {
+    MV_CHECK_ARG(a.mode == MV_GEMM_LINEAR || a.mode == MV_GEMM_HEAD_CONV,
+                 "mv_gemm_bf16: conv A operand only with MV_GEMM_LINEAR / MV_GEMM_HEAD_CONV");
+    MV_CHECK_ARG(a.conv_stride == 1 || a.conv_stride == 2, "mv_gemm_bf16: conv stride must be 1 or 2");
+    MV_CHECK_ARG(a.conv_c0 > 0 && a.conv_c0 % 8 == 0 && a.conv_c1 % 8 == 0 && (a.conv_c1 == 0 || a.a2),
+                 "mv_gemm_bf16: conv channel counts must be multiples of 8");
+    MV_CHECK_ARG(a.conv_w > 0 && a.conv_h > 0 && (a.conv_w % 128 == 0 || 128 % a.conv_w == 0) &&
+                     (a.conv_h * a.conv_w) % 128 == 0,
+                 "mv_gemm_bf16: conv output %dx%d must tile into 128-pixel row blocks", a.conv_h, a.conv_w);
+    MV_CHECK_ARG(a.m == a.conv_batch * a.conv_h * a.conv_w, "mv_gemm_bf16: conv M must be batch*H*W");
+    MV_CHECK_ARG(a.k == 9 * 64 * ((a.conv_c0 + 63) / 64 + (a.conv_c1 + 63) / 64),
+                 "mv_gemm_bf16: conv K must be 9 taps x 64-padded channel blocks (got %d)", a.k);
+  }
+  MV_CHECK_ARG(a.mode == MV_GEMM_HEAD_CONV || a.mode == MV_GEMM_HEAD_GATE || a.ldo % (a.out_f32 ? 4 : 8) == 0,
+               "mv_gemm_bf16: ldo alignment");
   MV_CHECK_ARG((reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "mv_gemm_bf16: out must be 16-byte aligned");
   MV_CHECK_ARG(!a.resid || ((reinterpret_cast<uintptr_t>(a.resid) & 15) == 0 && a.ldr % 4 == 0), "mv_gemm_bf16: resid alignment");
   MV_CHECK_ARG(!a.aux || ((reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && a.ldaux % 8 == 0), "mv_gemm_bf16: aux alignment");
@@ -397,6 +523,15 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
     case MV_GEMM_SWIGLU_BWD:
       MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
       return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
+    case MV_GEMM_HEAD_CONV:
+      MV_CHECK_ARG(a.conv && a.conv_c1 == 0 && a.conv_c0 <= 64 && a.conv_stride == 1 && a.n >= 1 && a.n <= 16 && a.shift &&
+                       a.in2 && a.ldin2 >= a.n,
+                   "mv_gemm_bf16(HEAD_CONV): one <=64-channel NHWC source, <=16 heads, bias (shift) and gates (in2) required");
+      return launch_gemm<16, MV_GEMM_HEAD_CONV>(a, stream);
+    case MV_GEMM_HEAD_GATE:
+      MV_CHECK_ARG(a.n % 16 == 0 && a.n <= 256 && a.scale && a.shift && a.in2 && a.resid && !a.out_f32,
+                   "mv_gemm_bf16(HEAD_GATE): N = 16*heads <= 256; scale, shift, in2 (w2) and resid (b2) required");
+      return launch_gemm<256, MV_GEMM_HEAD_GATE>(a, stream);
     case MV_GEMM_LINEAR: {
       int bn = a.block_n;
       if (bn == 0) {

@@ -31,7 +31,8 @@ int device_sms() { return g_sms; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* ptr, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                const uint32_t* elem_strides) {
   if (!g_encode) {
     set_error("mv_init() has not been called (no TMA encoder)");
     return MV_ERR_DEVICE;
@@ -43,7 +44,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* p
   for (uint32_t i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = g_encode(out, dt, rank, ptr, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -106,6 +107,36 @@ const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t col
   if (g_tmaps.size() > 65536) {  // unbounded growth guard: descriptors are tiny, but pointers may churn
     for (auto& kv : g_tmaps) free(kv.second);
     g_tmaps.clear();
+  }
+  g_tmaps.emplace(key, tm);
+  return tm;
+}
+
+const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, int c, int tw, int th, int stride) {
+  // key reuse: rows = batch<<32|h, cols = w<<32|c, ld = stride, box = (th, tw) with a tag bit so 2-D maps never collide
+  TmapKey key{ptr, ((uint64_t)batch << 32) | (uint32_t)h, ((uint64_t)w << 32) | (uint32_t)c, (uint64_t)stride | (1ull << 63),
+              (uint32_t)th, (uint32_t)tw};
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (c % 8)) {
+    set_error("NHWC TMA source must be 16-byte aligned with C %% 8 == 0 (ptr %p C %d)", ptr, c);
+    return nullptr;
+  }
+  void* mem = nullptr;
+  if (posix_memalign(&mem, 64, sizeof(CUtensorMap)) != 0) {
+    set_error("out of host memory");
+    return nullptr;
+  }
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(mem);
+  uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+  uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
+  uint32_t box[4] = {64, (uint32_t)(tw * stride), (uint32_t)(th * stride), 1};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  if (encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                  CU_TENSOR_MAP_SWIZZLE_128B, es) != MV_OK) {
+    free(mem);
+    return nullptr;
   }
   g_tmaps.emplace(key, tm);
   return tm;

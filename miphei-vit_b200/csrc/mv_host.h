@@ -18,9 +18,13 @@ void count_launch(int n = 1);
 // Cached by (ptr, rows, cols, ld, box); returns nullptr and sets the error string on failure.
 const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                     uint32_t box_cols = 64);
+// 4-D NHWC bf16 map [B, H, W, C] with box {64 channels, tw*stride, th*stride, 1} traversed with element stride
+// `stride` in W and H (tw x th pixels land in smem as 128-byte rows, 128-byte swizzle). Cached.
+const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, int c, int tw, int th, int stride);
 // Generic encoder (rank <= 5) for kernels that need other layouts; not cached.
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* ptr, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                const uint32_t* elem_strides = nullptr);
 
 #define MV_CHECK_ARG(cond, ...)       \
   do {                                \

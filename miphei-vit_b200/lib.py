@@ -30,7 +30,10 @@ class GemmArgs(ctypes.Structure):
         ("resid", c_void_p), ("ldr", c_i64),
         ("in2", c_void_p), ("ldin2", c_i64),
         ("rows_per_group", c_i32), ("group_stride", c_i32), ("row_offset", c_i32), ("resid_row_mod", c_i32),
-        ("block_n", c_i32), ("reserved", c_i32),
+        ("block_n", c_i32), ("conv", c_i32),
+        ("a2", c_void_p),
+        ("conv_batch", c_i32), ("conv_h", c_i32), ("conv_w", c_i32), ("conv_stride", c_i32),
+        ("conv_c0", c_i32), ("conv_c1", c_i32),
     ]
 
 
@@ -48,6 +51,10 @@ _SIGNATURES = {
     "mv_layernorm_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
                                  c_void_p, c_i64, c_int, c_int, c_float, c_void_p]),
     "mv_attn_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "mv_prep_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv_fill_prefix": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_tokens_to_map": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -6,7 +6,7 @@ import torch
 
 from . import lib as _lib
 
-GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD = 0, 1, 2
+GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD, GEMM_HEAD_GATE, GEMM_HEAD_CONV = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU = 0, 1
 
 
@@ -32,30 +32,54 @@ def _rowmajor(t, name):
 
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
-         resid_row_mod=False, block_n=0):
+         resid_row_mod=False, block_n=0, conv=None, out_kind=None):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
     lib = _lib_for(a)
-    _rowmajor(a, "a"), _rowmajor(b, "b")
+    _rowmajor(b, "b")
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    M, K = a.shape
     N, Kb = b.shape
-    assert K == Kb, (a.shape, b.shape)
+    a2 = None
+    if conv is not None:
+        # a (and optionally conv["a2"]) are contiguous NHWC maps [B, Hin, Win, C]; conv = dict(stride=1|2, a2=None)
+        stride = conv.get("stride", 1)
+        a2 = conv.get("a2")
+        assert a.dim() == 4 and a.is_contiguous() and (a2 is None or (a2.is_contiguous() and a2.shape[:3] == a.shape[:3]))
+        Bc, Hin, Win, C0 = a.shape
+        C1 = a2.shape[3] if a2 is not None else 0
+        Ho, Wo = Hin // stride, Win // stride
+        M, K = Bc * Ho * Wo, 9 * 64 * ((C0 + 63) // 64 + (C1 + 63) // 64)
+    else:
+        _rowmajor(a, "a")
+        M, K = a.shape
+    assert K == Kb, ((M, K), b.shape)
     if mode == GEMM_SWIGLU:
         out_cols = N // 2
     elif mode == GEMM_SWIGLU_BWD:
         out_cols = 2 * N
     else:
         out_cols = N
-    if out is None:
-        out = torch.empty((out_rows if out_rows is not None else M, out_cols), dtype=out_dtype, device=a.device)
-    _rowmajor(out, "out")
+    if mode == GEMM_HEAD_GATE:
+        out_cols = N // 16
+    if mode == GEMM_HEAD_CONV:
+        if out is None:
+            out = torch.empty((Bc, N, Ho, Wo), dtype=out_dtype, device=a.device)
+        assert out.is_contiguous()
+    else:
+        if out is None:
+            out = torch.empty((out_rows if out_rows is not None else M, out_cols), dtype=out_dtype, device=a.device)
+        _rowmajor(out, "out")
     args = _lib.GemmArgs()
-    args.a, args.lda = a.data_ptr(), a.stride(0)
+    args.a, args.lda = a.data_ptr(), (a.stride(0) if conv is None else 0)
+    if conv is not None:
+        args.conv = 1
+        args.a2 = a2.data_ptr() if a2 is not None else None
+        args.conv_batch, args.conv_h, args.conv_w, args.conv_stride = Bc, Ho, Wo, stride
+        args.conv_c0, args.conv_c1 = C0, C1
     args.b, args.ldb = b.data_ptr(), b.stride(0)
     args.m, args.n, args.k = M, N, K
     args.mode, args.act = mode, act
-    args.out_f32 = 1 if out.dtype == torch.float32 else 0
-    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    args.out_f32 = 1 if out.dtype == torch.float32 else (2 if out.dtype == torch.uint8 else 0)
+    args.out, args.ldo = out.data_ptr(), (out.stride(0) if mode != GEMM_HEAD_CONV else 0)
     if aux is not None:
         args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
     if scale is not None:
@@ -66,10 +90,10 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
         args.shift = shift.data_ptr()
     if resid is not None:
         assert resid.dtype == torch.float32
-        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+        args.resid, args.ldr = resid.data_ptr(), (resid.stride(0) if resid.dim() == 2 else 0)
     if in2 is not None:
-        assert in2.dtype == torch.bfloat16
-        args.in2, args.ldin2 = in2.data_ptr(), in2.stride(0)
+        assert in2.dtype == (torch.float32 if mode == GEMM_HEAD_GATE else torch.bfloat16)
+        args.in2, args.ldin2 = in2.data_ptr(), (in2.stride(0) if in2.dim() == 2 else 0)
     args.rows_per_group, args.group_stride, args.row_offset = rows_per_group, group_stride, row_offset
     args.resid_row_mod = 1 if resid_row_mod else 0
     args.block_n = block_n
@@ -120,3 +144,44 @@ def attn_fwd(qkv, batch, n_tok, heads, *, out=None, want_lse=False, scale=None):
     _lib.check(lib.mv_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), _ptr(lse), batch, n_tok, heads,
                                float(scale), _stream()), "mv_attn_fwd")
     return (out, lse) if want_lse else out
+
+
+def prep_input(x, want_image=True, want_patches=True):
+    """x fp32 NCHW -> (NHWC bf16 image padded to 8 channels, patch matrix [B*g*g, 592]) (mv_prep_input)."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3 and x.shape[2] == x.shape[3]
+    B, _, S, _ = x.shape
+    g = S // 14
+    img = torch.empty((B, S, S, 8), dtype=torch.bfloat16, device=x.device) if want_image else None
+    pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=x.device) if want_patches else None
+    _lib.check(lib.mv_prep_input(_ptr(x), _ptr(img), _ptr(pm), B, S, 592, _stream()), "mv_prep_input")
+    return img, pm
+
+
+def fill_prefix(x_res, prefix, batch, n_tok):
+    lib = _lib_for(x_res)
+    assert x_res.dtype == torch.float32 and prefix.dtype == torch.float32 and prefix.is_contiguous()
+    _lib.check(lib.mv_fill_prefix(_ptr(x_res), x_res.stride(0), _ptr(prefix), batch, n_tok, prefix.shape[0],
+                                  prefix.shape[1], _stream()), "mv_fill_prefix")
+
+
+def tokens_to_map(tokens, batch, n_tok, prefix, grid, target, out=None):
+    """final-norm tokens bf16 [B*n_tok, D] -> NHWC bf16 [B, target, target, D], bicubic (mv_tokens_to_map)."""
+    lib = _lib_for(tokens)
+    D = tokens.shape[1]
+    if out is None:
+        out = torch.empty((batch, target, target, D), dtype=torch.bfloat16, device=tokens.device)
+    _lib.check(lib.mv_tokens_to_map(_ptr(tokens), tokens.stride(0), _ptr(out), batch, n_tok, prefix, grid, target, D,
+                                    _stream()), "mv_tokens_to_map")
+    return out
+
+
+def upsample2x(x, out=None):
+    """bilinear x2, NHWC bf16 (mv_upsample2x)."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    B, h, w, C = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * h, 2 * w, C), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.mv_upsample2x(_ptr(x), _ptr(out), B, h, w, C, _stream()), "mv_upsample2x")
+    return out
