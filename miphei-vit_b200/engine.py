@@ -1,0 +1,298 @@
+"""Execution engine of the MIPHEI-ViT generator on B200: packs the module's weights into kernel layouts and runs the
+forward pass (and, in training, the backward pass) as a fixed sequence of hand-written sm_100a kernels.
+
+Data layout in HBM
+  residual stream      fp32 [B*N, D]   (token-major; N = (S//14)^2 + 5)
+  GEMM operands        bf16 row-major, K contiguous; LayerNorm output carries 16 extra columns (x @ [A_q | A_v]) so that
+                       the rank-8 LoRA updates of q and v ride inside the QKV GEMM (K = D + 16) — src/generators/lora.py:29-33
+  decoder maps         bf16 NHWC; 3x3 convs are implicit GEMMs over TMA tiles; BatchNorm folded into the epilogue in eval
+  output               NCHW [B, C, S, S] fp32 (or bf16 / uint8 sink) written by the fused heads kernel
+"""
+import torch
+
+from . import ops, packing
+
+PATCH = 14
+NUM_PREFIX = 5
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+class _Workspace:
+    """Activation buffers for one batch size (stable addresses: TMA descriptors are cached by pointer)."""
+
+    def __init__(self, eng, B):
+        dev = eng.device
+        D, H, N, S = eng.D, eng.H, eng.N, eng.S
+        M = B * N
+        t = S // 16
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+        self.B, self.M = B, M
+        self.x_in = e((B, 3, S, S), f32)
+        self.img8 = e((B, S, S, 8), bf)
+        self.pm = e((B * eng.g * eng.g, 592), bf)
+        self.x = e((M, D), f32)
+        self.xn_ext = torch.zeros((M, D + 64), dtype=bf, device=dev)
+        self.qkv = e((M, 3 * D), bf)
+        self.o = e((M, D), bf)
+        self.xn2 = e((M, D), bf)
+        self.u = e((M, H), bf)
+        self.tok = e((M, D), bf)
+        self.fmap = e((B, t, t, D), bf)
+        self.d = [self.img8, e((B, S // 2, S // 2, 48), bf), e((B, S // 4, S // 4, 96), bf), e((B, S // 8, S // 8, 192), bf)]
+        fus_in = [D, 256, 128, 64]
+        fus_out = [256, 128, 64, 32]
+        self.up = [e((B, 2 * t * 2 ** i, 2 * t * 2 ** i, fus_in[i]), bf) for i in range(4)]
+        self.f = [e((B, 2 * t * 2 ** i, 2 * t * 2 ** i, fus_out[i]), bf) for i in range(4)]
+        self.gate = e((B * S * S, eng.heads_out), bf)
+        self.out = e((B, eng.heads_out, S, S), f32)
+        self.graph = None
+
+
+class MipheiEngine:
+    def __init__(self, model):
+        self.model = model
+        self._packed = False
+        self._train_versions = None
+        self._ws = {}
+        self.use_graphs = True
+
+    # ------------------------------------------------------------------ geometry
+    def _geometry(self):
+        vit = self.model.encoder.vit
+        self.S = vit.patch_embed.img_size[0]
+        self.g = vit.patch_embed.grid_size[0]
+        self.N = self.g * self.g + NUM_PREFIX
+        self.D = vit.embed_dim
+        self.heads = vit.num_heads
+        self.H = vit.hidden
+        self.depth = len(vit.blocks)
+        self.heads_out = self.model.decoder.num_heads
+        assert self.D == self.heads * 64, "the attention kernel is specialised for head_dim 64"
+        assert self.D % 128 == 0 and self.H % 128 == 0
+        assert self.heads_out <= 16, "fused heads kernel handles up to 16 output channels"
+        self.device = self.model.encoder.vit.pos_embed.device
+
+    def invalidate(self):
+        self._packed = False
+        self._train_versions = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------ packing
+    def _trainable_version(self):
+        return tuple(p._version for p in self._trainables) + tuple(
+            b._version for b in self._bn_buffers) + (self.model.training,)
+
+    def _pack_frozen(self):
+        self._geometry()
+        if self.device.type != "cuda":
+            raise ops._lib.MipheiB200Error("the MIPHEI-ViT B200 engine needs its parameters on a CUDA device (got %s); "
+                                           "there is no CPU path" % self.device)
+        vit = self.model.encoder.vit
+        D = self.D
+        with torch.no_grad():
+            w = torch.zeros((D, 592), dtype=torch.float32, device=self.device)
+            w[:, :588] = vit.patch_embed.proj.weight.detach().float().flatten(1)
+            self.pe_w = w.to(torch.bfloat16)
+            self.pe_b = _f32(vit.patch_embed.proj.bias)
+            self.pos = _f32(vit.pos_embed[0])
+            self.prefix = torch.cat([_f32(vit.cls_token[0]), _f32(vit.reg_token[0])], 0).contiguous()
+            self.blocks = []
+            for blk in vit.blocks:
+                q = blk.attn.qkv
+                pb = {}
+                wext = torch.zeros((3 * D, D + 64), dtype=torch.bfloat16, device=self.device)
+                wext[:, :D] = q.qkv.weight.detach()
+                pb["wqkv_ext"] = wext
+                pb["bqkv"] = _f32(q.qkv.bias)
+                pb["acat"] = torch.zeros((16, D), dtype=torch.bfloat16, device=self.device)
+                pb["n1w"], pb["n1b"] = _f32(blk.norm1.weight), _f32(blk.norm1.bias)
+                pb["n2w"], pb["n2b"] = _f32(blk.norm2.weight), _f32(blk.norm2.bias)
+                pb["wproj"] = _bf16(blk.attn.proj.weight)
+                g1 = _f32(blk.ls1.gamma)
+                pb["g1"], pb["g1b"] = g1, (g1 * _f32(blk.attn.proj.bias)).contiguous()
+                pb["w1"], pb["b1"] = _bf16(blk.mlp.fc1.weight), _f32(blk.mlp.fc1.bias)
+                pb["w2"] = _bf16(blk.mlp.fc2.weight)
+                g2 = _f32(blk.ls2.gamma)
+                pb["g2"], pb["g2b"] = g2, (g2 * _f32(blk.mlp.fc2.bias)).contiguous()
+                pb["lora"] = (q.lora_q, q.lora_v)
+                self.blocks.append(pb)
+            self.nw, self.nb = _f32(vit.norm.weight), _f32(vit.norm.bias)
+        self._trainables = [p for p in self.model.parameters() if p.requires_grad]
+        self._bn_buffers = [b for n, b in self.model.decoder.named_buffers() if n.endswith(("running_mean", "running_var"))]
+        self._packed = True
+        self._train_versions = None
+
+    def _pack_trainable(self):
+        """LoRA columns of the extended QKV weight + decoder weights (BatchNorm folded with running statistics)."""
+        D = self.D
+        dec = self.model.decoder
+        with torch.no_grad():
+            for pb in self.blocks:
+                lq, lv = pb["lora"]
+                pb["acat"][:8] = lq.A.detach().t()
+                pb["acat"][8:] = lv.A.detach().t()
+                pb["wqkv_ext"][:D, D:D + 8] = (lq.alpha * lq.B.detach()).t()
+                pb["wqkv_ext"][2 * D:, D + 8:D + 16] = (lv.alpha * lv.B.detach()).t()
+            self.cs = []
+            for i, m in enumerate(dec.convstream.convs):
+                cin = m.conv.weight.shape[1]
+                sc, sh = packing.fold_bn_eval(m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var, m.bn.eps)
+                self.cs.append((packing.pack_conv3x3(m.conv.weight, [cin]), sc, sh))
+            self.fu = []
+            skip_ch = [192, 96, 48, 3]
+            for i, m in enumerate(dec.fusion_blks):
+                w = m.conv.conv.weight
+                sc, sh = packing.fold_bn_eval(m.conv.bn.weight, m.conv.bn.bias, m.conv.bn.running_mean,
+                                              m.conv.bn.running_var, m.conv.bn.eps)
+                self.fu.append((packing.pack_conv3x3(w, [skip_ch[i], w.shape[1] - skip_ch[i]]), sc, sh))
+            hps = []
+            for h in range(self.heads_out):
+                sh_ = getattr(dec, "segmentation_head_%d" % h)
+                psi = sh_[0].psi
+                hps.append(dict(psi0_w=psi[0].weight, psi0_b=psi[0].bias,
+                                bn=(psi[1].weight, psi[1].bias, psi[1].running_mean, psi[1].running_var),
+                                psi3_w=psi[3].weight, psi3_b=psi[3].bias, conv_w=sh_[1].weight, conv_b=sh_[1].bias))
+            self.hd = packing.pack_heads(hps)
+        self._train_versions = self._trainable_version()
+
+    def _ensure_packed(self):
+        if not self._packed:
+            self._pack_frozen()
+        if self._train_versions != self._trainable_version():
+            self._pack_trainable()
+            for ws in self._ws.values():
+                ws.graph = None  # captured graphs bake nothing weight-dependent except pointers, which are stable;
+                # kept simple: re-capture after a weight update
+
+    def _workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = _Workspace(self, B)
+            self._ws[B] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward pieces (eval)
+    def _encode_tokens(self, ws):
+        B, N, D, g = ws.B, self.N, self.D, self.g
+        ops.prep_input(ws.x_in, img=ws.img8, pm=ws.pm)
+        ops.fill_prefix(ws.x, self.prefix, B, N)
+        ops.gemm(ws.pm, self.pe_w, shift=self.pe_b, resid=self.pos, out=ws.x, rows_per_group=g * g, group_stride=N,
+                 row_offset=NUM_PREFIX, resid_row_mod=True)
+        xn = ws.xn_ext[:, :D]
+        xt = ws.xn_ext[:, D:D + 16]
+        xe = ws.xn_ext[:, :D + 16]
+        for pb in self.blocks:
+            ops.layernorm_fwd(ws.x, pb["n1w"], pb["n1b"], out=xn)
+            ops.gemm(xn, pb["acat"], out=xt)
+            ops.gemm(xe, pb["wqkv_ext"][:, :D + 16], shift=pb["bqkv"], out=ws.qkv)
+            ops.attn_fwd(ws.qkv, B, N, self.heads, out=ws.o)
+            ops.gemm(ws.o, pb["wproj"], scale=pb["g1"], shift=pb["g1b"], resid=ws.x, out=ws.x)
+            ops.layernorm_fwd(ws.x, pb["n2w"], pb["n2b"], out=ws.xn2)
+            ops.gemm(ws.xn2, pb["w1"], mode=ops.GEMM_SWIGLU, shift=pb["b1"], out=ws.u)
+            ops.gemm(ws.u, pb["w2"], scale=pb["g2"], shift=pb["g2b"], resid=ws.x, out=ws.x)
+        ops.layernorm_fwd(ws.x, self.nw, self.nb, out=ws.tok)
+        ops.tokens_to_map(ws.tok, B, N, NUM_PREFIX, g, self.S // 16, out=ws.fmap)
+
+    def _decode_maps(self, ws, out):
+        B, S = ws.B, self.S
+        for i in range(3):
+            w, sc, sh = self.cs[i]
+            ops.gemm(ws.d[i], w, conv=dict(stride=2), scale=sc, shift=sh, act=ops.ACT_RELU,
+                     out=ws.d[i + 1].view(-1, ws.d[i + 1].shape[3]))
+        f = ws.fmap
+        for i in range(4):
+            w, sc, sh = self.fu[i]
+            ops.upsample2x(f, out=ws.up[i])
+            ops.gemm(ws.d[3 - i], w, conv=dict(stride=1, a2=ws.up[i]), scale=sc, shift=sh, act=ops.ACT_RELU,
+                     out=ws.f[i].view(-1, ws.f[i].shape[3]))
+            f = ws.f[i]
+        hd = self.hd
+        ops.gemm(f.view(-1, 32), hd["gate_w"][:, :32], mode=ops.GEMM_HEAD_GATE, scale=hd["gate_scale"],
+                 shift=hd["gate_shift"], in2=hd["gate_w2"], resid=hd["gate_b2"], out=ws.gate)
+        ops.gemm(f, hd["conv_w"], mode=ops.GEMM_HEAD_CONV, conv=dict(stride=1), shift=hd["conv_b"], in2=ws.gate, out=out)
+
+    def _run_eval(self, ws, out):
+        self._encode_tokens(ws)
+        self._decode_maps(ws, out)
+
+    # ------------------------------------------------------------------ public entry points
+    def _out_dtype(self, x):
+        if torch.is_autocast_enabled():
+            return torch.get_autocast_dtype("cuda")
+        return x.dtype if x.dtype in (torch.float16, torch.bfloat16) else torch.float32
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise ops._lib.MipheiB200Error("MIPHEI-ViT B200 generator needs CUDA inputs (got %s); no CPU path" % x.device)
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.S or x.shape[3] != self.S:
+            raise AssertionError("Input size (%s) doesn't match model (%d)" % (tuple(x.shape), self.S))
+
+    def forward(self, x):
+        self._ensure_packed()
+        self._check_input(x)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._trainables)
+        if self.model.training or needs_grad:
+            from .autograd import miphei_train_forward
+            return miphei_train_forward(self, x)
+        return self.infer(x, out_dtype=self._out_dtype(x))
+
+    @torch.no_grad()
+    def infer(self, x, out_dtype=torch.float32, reuse_output=False):
+        """Eval-mode forward (BatchNorm running statistics). out_dtype: float32 | bfloat16 | float16 | uint8 (sink)."""
+        self._ensure_packed()
+        self._check_input(x)
+        B = x.shape[0]
+        ws = self._workspace(B)
+        ws.x_in.copy_(x)  # also converts fp16/bf16 inputs to fp32
+        direct = out_dtype in (torch.float32,)
+        if out_dtype == torch.uint8:
+            if not hasattr(ws, "out_u8"):
+                ws.out_u8 = torch.empty((B, self.heads_out, self.S, self.S), dtype=torch.uint8, device=self.device)
+                ws.graph_u8 = None
+            out_buf, gkey = ws.out_u8, "graph_u8"
+        else:
+            out_buf, gkey = ws.out, "graph"
+        if self.use_graphs:
+            gr = getattr(ws, gkey)
+            if gr is None:
+                # warm-up outside capture (module load, descriptor creation, smem attribute calls)
+                self._run_eval(ws, out_buf)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._run_eval(ws, out_buf)
+                setattr(ws, gkey, gr)
+                self.launches_per_forward = None
+            gr.replay()
+        else:
+            self._run_eval(ws, out_buf)
+        if reuse_output:
+            return out_buf if direct or out_dtype == torch.uint8 else out_buf.to(out_dtype)
+        return out_buf.clone() if direct or out_dtype == torch.uint8 else out_buf.to(out_dtype)
+
+    @torch.no_grad()
+    def encode(self, x):
+        self._ensure_packed()
+        self._check_input(x)
+        ws = self._workspace(x.shape[0])
+        ws.x_in.copy_(x)
+        self._encode_tokens(ws)
+        return ws.fmap.permute(0, 3, 1, 2).to(self._out_dtype(x))  # NCHW view over channel-last memory
+
+    @torch.no_grad()
+    def decode(self, features, images):
+        self._ensure_packed()
+        ws = self._workspace(images.shape[0])
+        ws.x_in.copy_(images)
+        ops.prep_input(ws.x_in, img=ws.img8, want_patches=False)
+        ws.fmap.copy_(features.permute(0, 2, 3, 1))
+        self._decode_maps(ws, ws.out)
+        return ws.out.to(self._out_dtype(images))

@@ -146,14 +146,16 @@ def attn_fwd(qkv, batch, n_tok, heads, *, out=None, want_lse=False, scale=None):
     return (out, lse) if want_lse else out
 
 
-def prep_input(x, want_image=True, want_patches=True):
+def prep_input(x, want_image=True, want_patches=True, img=None, pm=None):
     """x fp32 NCHW -> (NHWC bf16 image padded to 8 channels, patch matrix [B*g*g, 592]) (mv_prep_input)."""
     lib = _lib_for(x)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3 and x.shape[2] == x.shape[3]
     B, _, S, _ = x.shape
     g = S // 14
-    img = torch.empty((B, S, S, 8), dtype=torch.bfloat16, device=x.device) if want_image else None
-    pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=x.device) if want_patches else None
+    if img is None and want_image:
+        img = torch.empty((B, S, S, 8), dtype=torch.bfloat16, device=x.device)
+    if pm is None and want_patches:
+        pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=x.device)
     _lib.check(lib.mv_prep_input(_ptr(x), _ptr(img), _ptr(pm), B, S, 592, _stream()), "mv_prep_input")
     return img, pm
 

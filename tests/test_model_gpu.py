@@ -1,0 +1,86 @@
+"""End-to-end parity of the B200 generator against the CPU oracle and the committed reference goldens (eval mode)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import model as om  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# parity bar of the north star: Pearson >= 0.999 on predictions; per-channel max relative error stated here
+PEARSON_MIN = 0.999
+MAX_REL_ERR = 0.05  # max |got - ref| per channel / max |ref| of that channel (bf16 operands, fp32 accumulation)
+
+
+def build(cfg, sd, train=False):
+    from miphei_vit_b200.generators.mipheivit import get_vitmatte
+
+    m = get_vitmatte("hoptimus0", cfg.img_size, cfg.out_chans, use_lora=True, embed_dim=cfg.embed_dim, depth=cfg.depth,
+                     num_heads=cfg.num_heads, hidden=cfg.hidden)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    return m.train() if train else m.eval()
+
+
+def check_pred(got, ref):
+    got = got.float().cpu()
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all()
+    p = om.pearson(got, ref)
+    rel = max(om.per_channel_max_rel_err(got, ref))
+    assert p >= PEARSON_MIN, "pearson %.6f" % p
+    assert rel <= MAX_REL_ERR, "max rel err %.4f" % rel
+    return p, rel
+
+
+@pytest.mark.parametrize("name", ["tiny128", "small16ch"])
+def test_infer_matches_reference_golden(name):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
+    cfg = om.Config(**g["config"])
+    sd = om.init_state_dict(cfg, seed=g["weight_seed"], perturb=True)
+    model = build(cfg, sd)
+    x = om.normalize_tiles(om.synthetic_tiles_u8(g["batch"], cfg.img_size, seed=g["input_seed"]))
+    with torch.no_grad():
+        got = model(x.cuda())
+        feats = model.encoder(x.cuda())
+    check_pred(got, g["pred_eval"])
+    check_pred(feats, g["features_eval"])
+    # second call goes through the captured CUDA graph: must be identical
+    with torch.no_grad():
+        again = model(x.cuda())
+    assert torch.equal(again, got)
+    # uint8 sink (src/callbacks.py:345-346): +-1 LSB of the truncated reference mapping, a few more where bf16 error
+    # crosses an integer boundary
+    u8 = model.engine.infer(x.cuda(), out_dtype=torch.uint8).cpu()
+    ref8 = (((g["pred_eval"] + 0.9) / 1.8).clamp(0, 1) * 255).to(torch.uint8)
+    assert (u8.int() - ref8.int()).abs().max().item() <= 8
+    assert (u8.int() - ref8.int()).abs().float().mean().item() < 0.6
+
+
+def test_infer_full_size_matches_oracle():
+    """ViT-g/14 (1.13 B parameters), 256 px, 16 channels, batch 2 — BASELINE config geometry."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg = om.Config()
+    sd = om.init_state_dict(cfg, seed=0, perturb=True)
+    model = build(cfg, sd)
+    x = om.normalize_tiles(om.synthetic_tiles_u8(2, cfg.img_size, seed=1234))
+    with torch.no_grad():
+        ref = om.miphei_forward(sd, x, cfg, training=False)
+        got = model(x.cuda())
+        half = model(x.cuda().half())
+    p, rel = check_pred(got, ref)
+    print("full-size parity: pearson %.6f max-rel-err %.4f" % (p, rel))
+    assert half.dtype == torch.float16
+
+
+def test_cpu_input_fails_loudly():
+    cfg = om.Config(img_size=128, embed_dim=128, depth=1, num_heads=2, hidden=256, out_chans=2)
+    model = build(cfg, om.init_state_dict(cfg, seed=1))
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 128, 128))
+    with pytest.raises(AssertionError):
+        model(torch.zeros(1, 3, 256, 256, device="cuda"))
