@@ -47,11 +47,12 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
   static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
   static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -144,6 +145,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  float* staging_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::kStageBytes + 256);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -268,50 +270,170 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
 
-      if constexpr (MODE == MV_GEMM_LINEAR) {
-        constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+      if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
+        // TMEM (one row per lane) -> padded smem tile -> row-contiguous global accesses (coalesced residual read,
+        // output write); scale / shift are per column, so they are applied after the transpose (fixed per lane).
+        float* stg = staging_all + quad * (32 * 36);
+        const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int n0 = n_blk * BLOCK_N + c * 32;
+          if (p.out_f32) {
+            const int col = (lane & 7) * 4;
+            const int nn = n0 + col;
+            if (nn < p.n) {
+              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
+              if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
+              // all residual loads are issued before the first store: out may alias resid (in-place residual update),
+              // so the compiler cannot hoist loads over stores by itself
+              long long orow_[8], rrow_[8];
+              float4 q_[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int mm = m_warp + it * 4 + (lane >> 3);
+                long long orow = mm, rrow = mm;
+                if (p.rows_per_group > 0) {
+                  const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
+                  orow = (long long)g * p.group_stride + rr + p.row_offset;
+                  rrow = p.resid_row_mod ? rr : orow;
+                }
+                orow_[it] = orow;
+                rrow_[it] = rrow;
+                q_[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.resid && mm < p.m) q_[it] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + nn);
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (lane >> 3);
+                const int mm = m_warp + r;
+                if (mm < p.m) {
+                  float4 a = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+                  a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+                  if (p.act == MV_ACT_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                  a.x += q_[it].x; a.y += q_[it].y; a.z += q_[it].z; a.w += q_[it].w;
+                  const long long orow = orow_[it];
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nn) = a;
+                  if (p.aux) {
+                    uint2 u;
+                    u.x = pack_bf16x2(a.x, a.y);
+                    u.y = pack_bf16x2(a.z, a.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + orow * p.ldaux + nn) = u;
+                  }
+                }
+              }
+            }
+          } else {
+            const int col = (lane & 3) * 8;
+            const int nn = n0 + col;
+            if (nn < p.n) {
+              float sc[8], sh[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+              if (p.scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + nn + 4));
+                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              }
+              if (p.shift) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + nn + 4));
+                sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+              }
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + (lane >> 2);
+                const int mm = m_warp + r;
+                if (mm < p.m) {
+                  const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+                  const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 36 + col + 4);
+                  float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    f[j] = f[j] * sc[j] + sh[j];
+                    if (p.act == MV_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+                  }
+                  long long orow = mm, rrow = mm;
+                  if (p.rows_per_group > 0) {
+                    const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
+                    orow = (long long)g * p.group_stride + rr + p.row_offset;
+                    rrow = p.resid_row_mod ? rr : orow;
+                  }
+                  if (p.resid) {
+                    const float* q = p.resid + rrow * p.ldr + nn;
+                    const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+                    f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w; f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
+                  }
+                  store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nn, f);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (MODE == MV_GEMM_LINEAR) {
+        constexpr int CH = 16;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / CH; ++c) {
           uint32_t v[CH];
-          if constexpr (CH == 32) tmem_ld32(taddr + c * CH, v);
-          else tmem_ld16(taddr + c * CH, v);
+          tmem_ld16(taddr + c * CH, v);
           tmem_ld_wait();
           if (row_ok) epilogue_linear_chunk<CH>(p, v, m, n_blk * BLOCK_N + c * CH);
         }
       } else if constexpr (MODE == MV_GEMM_SWIGLU) {
-        // tile columns [0,128) = gate, [128,256) = value for hidden units n_blk*128 ..
+        // tile columns [0,128) = gate, [128,256) = value for hidden units n_blk*128 ..; silu(g)*v is formed per thread,
+        // then transposed through smem so that every output row segment is written contiguously
         const int half = p.n / 2;
+        float* stg = staging_all + quad * (32 * 36);
+        const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
+        auto stage_and_store = [&](const float* f32vals, __nv_bfloat16* dst, long long ld, int col0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 36 + j * 4) =
+                make_float4(f32vals[4 * j], f32vals[4 * j + 1], f32vals[4 * j + 2], f32vals[4 * j + 3]);
+          __syncwarp();
+          const int col = (lane & 3) * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int mm = m_warp + r;
+            if (mm < p.m) {
+              const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+              const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 36 + col + 4);
+              const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              store_bf16x8(dst + (long long)mm * ld + col0 + col, f);
+            }
+          }
+          __syncwarp();
+        };
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t g[32], u[32];
           tmem_ld32(taddr + c * 32, g);
           tmem_ld32(taddr + 128 + c * 32, u);
           tmem_ld_wait();
-          if (row_ok) {
-            const int j0 = n_blk * 128 + c * 32;
+          const int j0 = n_blk * 128 + c * 32;
+          float fg[32], fv[32], fo[32];
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              const int jj = j0 + j8 * 8;
-              float fg[8], fv[8], fo[8];
-              float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + jj));
-              float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + jj + 4));
-              float4 c0 = __ldg(reinterpret_cast<const float4*>(p.shift + half + jj));
-              float4 c1 = __ldg(reinterpret_cast<const float4*>(p.shift + half + jj + 4));
-              const float bg[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              const float bv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + j0 + j4 * 4));
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.shift + half + j0 + j4 * 4));
+            fg[4 * j4 + 0] = __uint_as_float(g[4 * j4 + 0]) + b0.x; fv[4 * j4 + 0] = __uint_as_float(u[4 * j4 + 0]) + c0.x;
+            fg[4 * j4 + 1] = __uint_as_float(g[4 * j4 + 1]) + b0.y; fv[4 * j4 + 1] = __uint_as_float(u[4 * j4 + 1]) + c0.y;
+            fg[4 * j4 + 2] = __uint_as_float(g[4 * j4 + 2]) + b0.z; fv[4 * j4 + 2] = __uint_as_float(u[4 * j4 + 2]) + c0.z;
+            fg[4 * j4 + 3] = __uint_as_float(g[4 * j4 + 3]) + b0.w; fv[4 * j4 + 3] = __uint_as_float(u[4 * j4 + 3]) + c0.w;
+          }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                fg[j] = __uint_as_float(g[j8 * 8 + j]) + bg[j];
-                fv[j] = __uint_as_float(u[j8 * 8 + j]) + bv[j];
-                fo[j] = silu_f(fg[j]) * fv[j];
-              }
-              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo + jj, fo);
-              if (p.aux) {
-                __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)m * p.ldaux;
-                store_bf16x8(h + jj, fg);
-                store_bf16x8(h + half + jj, fv);
-              }
-            }
+          for (int j = 0; j < 32; ++j) fo[j] = silu_f(fg[j]) * fv[j];
+          stage_and_store(fo, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, j0);
+          if (p.aux) {
+            stage_and_store(fg, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, j0);
+            stage_and_store(fv, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, half + j0);
           }
         }
       } else if constexpr (MODE == MV_GEMM_HEAD_GATE) {
@@ -547,7 +669,7 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
             const int t = mb * ((a.n + b - 1) / b);
             return (double)((t + sms - 1) / sms) * b;  // time ~ waves * tile width
           };
-          bn = waves_cost(256) <= waves_cost(128) * 1.02 ? 256 : 128;
+          bn = waves_cost(256) <= waves_cost(128) * 1.25 ? 256 : 128;
         }
       }
       switch (bn) {
