@@ -64,6 +64,9 @@ void mv_reset_launch_count(void);
  *                      sum_c B[h, tap, c] f[b, y', x', c]) with g = in2 (bf16 [M, ldin2], the HEAD_GATE output).
  *                      out is NCHW: out_f32 = 1 fp32, 0 bf16, 2 uint8 through the inference sink mapping
  *                      ((p+0.9)/1.8).clamp(0,1)*255 truncated (src/callbacks.py:345-346).
+ *   MV_GEMM_NN_ATOMIC  out[M, N] (fp32, caller-zeroed) += A[M, K] . B[K, N] with B ROW-major [K, N] (the reduction index is
+ *                      the slow one: weight-gradient form, K = tokens / pixels), split-K across CTAs, fp32 atomics.
+ *                      Used for the LoRA gradients dA = x^T dT, dB = (xA)^T dQ (src/generators/lora.py:16-18).
  *
  * Implicit-GEMM 3x3 convolution (pad 1, stride 1|2; Basic_Conv3x3, src/generators/mipheivit.py:20-41): set conv = 1.
  * A is then read from one or two NHWC bf16 feature maps (channel concat: a = [B,Hin,Win,c0], a2 = [B,Hin,Win,c1],
@@ -71,7 +74,7 @@ void mv_reset_launch_count(void);
  * (NHWC), M = batch*conv_h*conv_w, and B is [N, 9 * 64 * (ceil(c0/64)+ceil(c1/64))]: per tap (ky,kx) the source-0
  * channels zero-padded to a multiple of 64, then the source-1 channels likewise.
  * ---------------------------------------------------------------------------------------------------------- */
-enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2, MV_GEMM_HEAD_GATE = 3, MV_GEMM_HEAD_CONV = 4 };
+enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2, MV_GEMM_HEAD_GATE = 3, MV_GEMM_HEAD_CONV = 4, MV_GEMM_NN_ATOMIC = 5 };
 enum { MV_ACT_NONE = 0, MV_ACT_RELU = 1 };
 
 typedef struct mv_gemm_args {
@@ -99,6 +102,8 @@ typedef struct mv_gemm_args {
   const void* a2;     /* second NHWC source (channel concat) or NULL */
   int32_t conv_batch, conv_h, conv_w, conv_stride; /* OUTPUT height/width */
   int32_t conv_c0, conv_c1;
+  int32_t reserved_splits; /* NN_ATOMIC: split-K factor, 0 = choose */
+  int32_t reserved2;
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
@@ -138,6 +143,49 @@ int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int batch, int n_
 int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid, int target,
                      int dim, void* stream);
 int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, void* stream);
+
+/* adjoint of mv_tokens_to_map: d_map NHWC bf16 [B,t,t,D] -> d_tokens bf16 [B*n_tok, D] (prefix rows zero) */
+int mv_tokens_to_map_bwd(const void* dmap, void* dtokens, int64_t ldt, int batch, int n_tok, int prefix, int grid,
+                         int target, int dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Self-attention backward (autograd of timm Attention's scaled_dot_product_attention), head_dim 64, any n_tok.
+ *   qkv / out / lse as saved by mv_attn_fwd, dout bf16 [B*n_tok, D]; dsum fp32 [B, heads, n_tok] workspace;
+ *   dqkv bf16 [B*n_tok, >= 3D] receives dq | dk | dv.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int64_t ldo, const void* dout, int64_t lddo,
+                const float* lse, float* dsum, void* dqkv, int64_t lddqkv, int batch, int n_tok, int heads, float scale,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LoRA gradients of one block (QkvWithLoRA, src/generators/lora.py:16-18,29-33): see csrc/lora.cu.
+ *   xn_ext bf16 [M, >= D+16]: LayerNorm output with T = xn [A_q | A_v] in columns D..D+15;
+ *   dqkv_ext bf16 [M, >= 3D+16]: dq | dk | dv with dT in columns 3D..3D+15.
+ *   dA_* fp32 [D, 8], dB_* fp32 [8, D] are overwritten.  workspace: 256-byte aligned.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t mv_lora_grads_workspace_bytes(int m, int d);
+int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_ext, int64_t ldq, int m, int d, float alpha,
+                  float* dA_q, float* dA_v, float* dB_q, float* dB_v, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss and optimiser.
+ *   mv_loss_fwd_bwd     mode 0: WeightedMSELoss (src/loss.py:54-57; weights NULL = plain MSE, get_mse_loss 41-44),
+ *                       mode 1: get_mae_loss (35-38), mode 2: L1_L2_Loss (113-123). pred/target/grad NCHW fp32
+ *                       [B, C, HW]; grad (optional) = grad_scale * dloss/dpred; loss: one fp32.
+ *   mv_grad_norm        global L2 norm of a flat fp32 gradient buffer + clip coefficient min(1, max_norm/(norm+1e-6))
+ *                       (clip_gradients(..., 1.0, "norm"), src/models.py:136); norm_out: 2 floats; workspace 1024 floats.
+ *   mv_adam_clip_step   torch.optim.Adam(betas, eps, weight_decay 0) update (src/models.py:361-362) on flat buffers with
+ *                       the gradient scaled by norm_coef[1] * grad_mul on the fly; `step` counts from 1.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t mv_loss_workspace_floats(int batch, int chans, int hw);
+int mv_loss_fwd_bwd(const float* pred, const float* target, float* grad, const float* weights, int batch, int chans, int hw,
+                    int mode, float lambda, float grad_scale, float* loss, float* workspace, int64_t workspace_floats,
+                    void* stream);
+int mv_grad_norm(const float* grads, int64_t n, float max_norm, float* norm_out, float* workspace, void* stream);
+int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* norm_coef, float grad_mul, float lr, float beta1, float beta2, float eps, int step,
+                      void* stream);
 
 #ifdef __cplusplus
 }

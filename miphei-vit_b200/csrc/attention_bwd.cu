@@ -1,0 +1,377 @@
+// Self-attention backward (head_dim 64, any N) on tcgen05 / TMEM: dQ, dK, dV from dO, the saved q/k/v rows and the
+// saved log-sum-exp.  Autograd counterpart of timm Attention.forward's F.scaled_dot_product_attention.
+//
+//   D[q]   = sum_d dO[q,d] * O[q,d]                                   (mv_attn_bwd_prep, HBM-bound)
+//   P      = exp(S * scale - LSE),  S = Q K^T                          (recomputed, never stored)
+//   dP     = dO V^T,   dS = P .* (dP - D) * scale
+//   dV     = P^T dO,   dK = dS^T Q,   dQ = dS K
+//
+// One templated persistent kernel, instantiated twice (no atomics, every output written once):
+//   DKV = true : work item = (image, head, 128-key block); the key block's K, V rows are the TMEM-lane ("row")
+//                operands, the kernel loops over 128-query tiles and accumulates dV, dK of the block in TMEM.
+//   DKV = false: work item = (image, head, 128-query tile); Q, dO are the row operands, the loop runs over key blocks and
+//                accumulates dQ.  (S and dP are recomputed by both instances: 7 MMAs per tile pair instead of 5.)
+// Per tile pair: X = R1 C1^T and Y = R2 C2^T (SS MMAs) -> 8 softmax warps turn X into P and Y into dS (bf16, written
+// back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A operand read from TMEM and the C tiles
+// re-read from the SAME smem tiles as MN-major operands.
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+
+namespace mv {
+
+constexpr int ATB_THREADS = 320;
+constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
+
+struct AttnBwdDev {
+  int n_tok, heads, dim, blocks;  // blocks = ceil(n_tok / 128)
+  int total_items;
+  float scale, scale_log2e;
+  const float* lse;    // [B, heads, n_tok]
+  const float* dsum;   // [B, heads, n_tok]
+  __nv_bfloat16* dqkv; // [B*n_tok, 3*dim]
+  long long lddqkv;
+};
+
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool DKV>
+__global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                  const __grid_constant__ CUtensorMap tmap_do,
+                                                                  const AttnBwdDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // smem: R tiles 2 stages x (R1 | R2), C tiles 2 stages x (C1 | C2), barriers, lse/D staging
+  const uint32_t sR = smem_base, sC = smem_base + 4 * ATB_TILE;
+  const uint32_t misc_off = 8 * ATB_TILE;
+  const uint32_t bar_base = smem_base + misc_off;
+  auto r_full = [&](int s) { return bar_base + 8u * s; };
+  auto r_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto c_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto c_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  const uint32_t bar_xy = bar_base + 8u * 8, bar_pd = bar_base + 8u * 9, bar_acc = bar_base + 8u * 10,
+                 acc_empty = bar_base + 8u * 11;
+  const uint32_t tmem_slot = bar_base + 8u * 12;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 12);
+  float* s_lse = reinterpret_cast<float*>(smem_gen + misc_off + 128);  // [128] (scaled by log2e)
+  float* s_dsum = s_lse + 128;                                          // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = (int)((long long)p.total_items * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)p.total_items * (blockIdx.x + 1) / gridDim.x);
+  const int nblk = p.blocks;
+  constexpr uint32_t COL_X = 0, COL_Y = 128, COL_A1 = 256, COL_A2 = 320;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(r_full(s), 1);
+      mbar_init(r_empty(s), 1);
+      mbar_init(c_full(s), 1);
+      mbar_init(c_empty(s), 1);
+    }
+    mbar_init(bar_xy, 1);
+    mbar_init(bar_pd, 256);
+    mbar_init(bar_acc, 1);
+    mbar_init(acc_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int rs = 0, cs = 0;
+      uint32_t rph = 0, cph = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int bh = t / nblk, ob = t - bh * nblk;  // outer block: key block (DKV) or query tile
+        const int b = bh / p.heads, h = bh - b * p.heads;
+        const int row0 = b * p.n_tok;
+        mbar_wait(r_empty(rs), rph ^ 1);
+        mbar_expect_tx(r_full(rs), 2 * ATB_TILE);
+        const uint32_t r1 = sR + rs * 2 * ATB_TILE, r2 = r1 + ATB_TILE;
+        if (DKV) {
+          tma_load_2d(r1, &tmap_qkv, r_full(rs), p.dim + h * 64, row0 + ob * 128);      // K_j
+          tma_load_2d(r2, &tmap_qkv, r_full(rs), 2 * p.dim + h * 64, row0 + ob * 128);  // V_j
+        } else {
+          tma_load_2d(r1, &tmap_qkv, r_full(rs), h * 64, row0 + ob * 128);              // Q_i
+          tma_load_2d(r2, &tmap_do, r_full(rs), h * 64, row0 + ob * 128);               // dO_i
+        }
+        if (++rs == 2) { rs = 0; rph ^= 1; }
+        for (int ib = 0; ib < nblk; ++ib) {
+          mbar_wait(c_empty(cs), cph ^ 1);
+          mbar_expect_tx(c_full(cs), 2 * ATB_TILE);
+          const uint32_t c1 = sC + cs * 2 * ATB_TILE, c2 = c1 + ATB_TILE;
+          if (DKV) {
+            tma_load_2d(c1, &tmap_qkv, c_full(cs), h * 64, row0 + ib * 128);            // Q_i
+            tma_load_2d(c2, &tmap_do, c_full(cs), h * 64, row0 + ib * 128);             // dO_i
+          } else {
+            tma_load_2d(c1, &tmap_qkv, c_full(cs), p.dim + h * 64, row0 + ib * 128);      // K_j
+            tma_load_2d(c2, &tmap_qkv, c_full(cs), 2 * p.dim + h * 64, row0 + ib * 128);  // V_j
+          }
+          if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int rs = 0, cs = 0;
+      uint32_t rph = 0, cph = 0, xph = 0, aph = 0;
+      const uint32_t idesc_xy = umma_idesc_bf16(128, 128);
+      const uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(r_full(rs), rph);
+        const uint32_t r1 = sR + rs * 2 * ATB_TILE, r2 = r1 + ATB_TILE;
+        const uint64_t dr1 = umma_desc_sw128(r1), dr2 = umma_desc_sw128(r2);
+        for (int ib = 0; ib < nblk; ++ib) {
+          mbar_wait(c_full(cs), cph);
+          tc_fence_after();
+          const uint32_t c1 = sC + cs * 2 * ATB_TILE, c2 = c1 + ATB_TILE;
+          const uint64_t dc1 = umma_desc_sw128(c1), dc2 = umma_desc_sw128(c2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_X, dr1 + 2 * k, dc1 + 2 * k, idesc_xy, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_Y, dr2 + 2 * k, dc2 + 2 * k, idesc_xy, k != 0);
+          umma_commit(bar_xy);
+          mbar_wait(bar_pd, xph);
+          if (ib == 0) mbar_wait(acc_empty, aph ^ 1);  // previous item's accumulators drained
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (DKV) {
+              const uint64_t dmn2 = umma_desc_sw128(c2 + k * 2048, 1024, 1024);
+              umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + k * 8, dmn2, idesc_acc, (ib | k) != 0);
+            }
+            const uint64_t dmn1 = umma_desc_sw128(c1 + k * 2048, 1024, 1024);
+            umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + k * 8, dmn1, idesc_acc, (ib | k) != 0);
+          }
+          umma_commit(c_empty(cs));
+          if (ib == nblk - 1) {
+            umma_commit(bar_acc);
+            umma_commit(r_empty(rs));
+          }
+          if (++cs == 2) { cs = 0; cph ^= 1; }
+          xph ^= 1;
+        }
+        if (++rs == 2) { rs = 0; rph ^= 1; }
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ===================== softmax-backward math + epilogue (8 warps) =====================
+    const int sw = warp - 2;
+    const int quad = warp & 3;
+    const int half = sw >> 2;
+    const int r = quad * 32 + lane;
+    const int tid = sw * 32 + lane;  // 0..255
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int n_tok = p.n_tok;
+    uint32_t xph = 0, aph = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int bh = t / nblk, ob = t - bh * nblk;
+      const int b = bh / p.heads, h = bh - b * p.heads;
+      const long long vec0 = (long long)bh * n_tok;
+      const int orow = ob * 128 + r;  // key (DKV) or query index of this thread's row
+      float lse_r = 0.f, dsum_r = 0.f;
+      if (!DKV && orow < n_tok) {
+        lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
+        dsum_r = p.dsum[vec0 + orow];
+      }
+      for (int ib = 0; ib < nblk; ++ib) {
+        if (DKV) {  // per-column (query) statistics of this inner tile
+          if (tid < 128) {
+            const int q = ib * 128 + tid;
+            s_lse[tid] = q < n_tok ? p.lse[vec0 + q] * 1.4426950408889634f : 0.f;
+          } else {
+            const int q = ib * 128 + tid - 128;
+            s_dsum[tid - 128] = q < n_tok ? p.dsum[vec0 + q] : 0.f;
+          }
+          nbar(1, 256);
+        }
+        mbar_wait(bar_xy, xph);
+        tc_fence_after();
+        uint32_t pp[2][16], pd[2][16];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = half * 64 + ci * 32;
+          uint32_t x[32], y[32];
+          tmem_ld32(trow + COL_X + c0, x);
+          tmem_ld32(trow + COL_Y + c0, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = c0 + 2 * j + e;
+              const int icol = ib * 128 + col;
+              const bool ok = orow < n_tok && icol < n_tok;
+              const float l2 = DKV ? s_lse[col] : lse_r;
+              const float dd = DKV ? s_dsum[col] : dsum_r;
+              const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
+              pv[e] = pr;
+              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd) * p.scale;
+            }
+            pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
+            pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
+          }
+        }
+        nbar(2, 256);  // every warp has finished reading X / Y: P and dS may overwrite them
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int pc = half * 32 + ci * 16;
+          if (DKV) tmem_st16(trow + COL_X + pc, pp[ci]);
+          tmem_st16(trow + COL_Y + pc, pd[ci]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_pd);
+        xph ^= 1;
+      }
+      // ---- epilogue: accumulators -> bf16 rows of dqkv
+      mbar_wait(bar_acc, aph);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      int col_base;
+      if (DKV) {  // half 0 stores dV (acc1), half 1 stores dK (acc2); 64 columns each
+        const uint32_t src = half == 0 ? COL_A1 : COL_A2;
+        tmem_ld32(trow + src, a0);
+        tmem_ld32(trow + src + 32, a1);
+        col_base = (half == 0 ? 2 * p.dim : p.dim) + h * 64;
+      } else {    // dQ: half 0 stores columns 0..31, half 1 columns 32..63
+        tmem_ld32(trow + COL_A2 + half * 32, a0);
+        col_base = h * 64 + half * 32;
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      if (orow < n_tok) {
+        __nv_bfloat16* dst = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + col_base;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(a0[8 * j + 0]), __uint_as_float(a0[8 * j + 1]));
+          u.y = pack_bf16x2(__uint_as_float(a0[8 * j + 2]), __uint_as_float(a0[8 * j + 3]));
+          u.z = pack_bf16x2(__uint_as_float(a0[8 * j + 4]), __uint_as_float(a0[8 * j + 5]));
+          u.w = pack_bf16x2(__uint_as_float(a0[8 * j + 6]), __uint_as_float(a0[8 * j + 7]));
+          reinterpret_cast<uint4*>(dst)[j] = u;
+        }
+        if (DKV) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(a1[8 * j + 0]), __uint_as_float(a1[8 * j + 1]));
+            u.y = pack_bf16x2(__uint_as_float(a1[8 * j + 2]), __uint_as_float(a1[8 * j + 3]));
+            u.z = pack_bf16x2(__uint_as_float(a1[8 * j + 4]), __uint_as_float(a1[8 * j + 5]));
+            u.w = pack_bf16x2(__uint_as_float(a1[8 * j + 6]), __uint_as_float(a1[8 * j + 7]));
+            reinterpret_cast<uint4*>(dst)[4 + j] = u;
+          }
+        }
+      }
+      aph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[b, h, q] = sum_d dO[q, h*64 + d] * O[q, h*64 + d]; one warp per (token row, 2 heads per pass)
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo,
+                                     const __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ dsum,
+                                     int batch, int n_tok, int heads) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)batch * n_tok) return;
+  const int b = (int)(row / n_tok), q = (int)(row - (long long)b * n_tok);
+  // each lane covers 8 consecutive channels; 32 lanes = 256 channels = 4 heads per iteration
+  for (int c0 = 0; c0 < heads * 64; c0 += 256) {
+    const int c = c0 + lane * 8;
+    float s = 0.f;
+    if (c < heads * 64) {
+      const uint4 a = *reinterpret_cast<const uint4*>(dout + row * lddo + c);
+      const uint4 o = *reinterpret_cast<const uint4*>(out + row * ldo + c);
+      const uint32_t* pa = &a.x;
+      const uint32_t* po = &o.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack_bf16x2(pa[j]), fo = unpack_bf16x2(po[j]);
+        s += fa.x * fo.x + fa.y * fo.y;
+      }
+    }
+    // reduce over the 8 lanes of one head
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const int h = c / 64;
+    if ((lane & 7) == 0 && h < heads) dsum[((long long)b * heads + h) * n_tok + q] = s;
+  }
+}
+
+}  // namespace mv
+
+// qkv [B*N, 3D] (saved forward input), out [B*N, D] (saved forward output), dout [B*N, D], lse [B, heads, N]
+// -> dqkv [B*N, 3D] (dq | dk | dv); dsum: fp32 workspace [B, heads, N].
+extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int64_t ldo, const void* dout, int64_t lddo,
+                           const float* lse, float* dsum, void* dqkv, int64_t lddqkv, int batch, int n_tok, int heads,
+                           float scale, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(qkv && out && dout && lse && dsum && dqkv && batch > 0 && heads > 0 && n_tok > 0, "mv_attn_bwd: null/empty");
+  MV_CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0, "mv_attn_bwd: leading dimensions must be multiples of 8");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long rows = (long long)batch * n_tok;
+  attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dout), lddo, reinterpret_cast<const __nv_bfloat16*>(out), ldo, dsum, batch,
+      n_tok, heads);
+  MV_CHECK_LAUNCH("attn_bwd_prep");
+  AttnBwdDev p;
+  p.n_tok = n_tok;
+  p.heads = heads;
+  p.dim = heads * 64;
+  p.blocks = (n_tok + 127) / 128;
+  p.total_items = batch * heads * p.blocks;
+  p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = lse;
+  p.dsum = dsum;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.lddqkv = lddqkv;
+  const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
+  const CUtensorMap* td = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 128);
+  if (!tq || !td) return MV_ERR_ARG;
+  const int smem = 8 * ATB_TILE + 128 + 2 * 128 * 4 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd): %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  int grid = device_sms() > 0 ? device_sms() : 148;
+  if (grid > p.total_items) grid = p.total_items;
+  attn_bwd_kernel<true><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, p);
+  MV_CHECK_LAUNCH("attn_bwd_dkv");
+  attn_bwd_kernel<false><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, p);
+  MV_CHECK_LAUNCH("attn_bwd_dq");
+  return MV_OK;
+}

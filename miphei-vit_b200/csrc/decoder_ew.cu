@@ -136,6 +136,56 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
   *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// Adjoint of tokens_to_map_kernel: d_tok[b, prefix + gy*g + gx, :] = sum_{oy,ox} Wy[oy,gy] Wx[ox,gx] d_map[b,oy,ox,:];
+// prefix-token rows get zero. One block per token row.
+__global__ void tokens_to_map_bwd_kernel(const __nv_bfloat16* __restrict__ dmap, int ntok, int prefix, int g, int t, int D,
+                                         float inv_scale, __nv_bfloat16* __restrict__ dtok, long long ldt) {
+  __shared__ float wy[64], wx[64];
+  const int tok = blockIdx.x % ntok, b = blockIdx.x / ntok;
+  __nv_bfloat16* dst = dtok + ((long long)b * ntok + tok) * ldt;
+  if (tok < prefix) {
+    for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int gy = (tok - prefix) / g, gx = (tok - prefix) % g;
+  if (threadIdx.x < 2 * t) {  // weight of output coordinate o on source coordinate gy (threads 0..t-1) / gx (t..2t-1)
+    const int o = threadIdx.x % t;
+    const int gsel = threadIdx.x < t ? gy : gx;
+    const float sc = (o + 0.5f) * inv_scale - 0.5f;
+    const int i0 = (int)floorf(sc);
+    float w[4];
+    cubic_coeffs(sc - i0, w);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (min(max(i0 - 1 + a, 0), g - 1) == gsel) acc += w[a];
+    (threadIdx.x < t ? wy : wx)[o] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = 0; oy < t; ++oy) {
+      if (wy[oy] == 0.f) continue;
+      for (int ox = 0; ox < t; ++ox) {
+        const float w = wy[oy] * wx[ox];
+        if (w == 0.f) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(dmap + (((long long)b * t + oy) * t + ox) * D + c);
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p1.x; acc[3] += w * p1.y;
+        acc[4] += w * p2.x; acc[5] += w * p2.y; acc[6] += w * p3.x; acc[7] += w * p3.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dst + c) = o;
+  }
+}
+
 // residual stream rows of the prefix tokens: x[b, j, :] = prefix[j, :] (cls + register tokens, no pos-embed:
 // timm _pos_embed with no_embed_class=True)
 __global__ void fill_prefix_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ prefix, int B, int ntok,
@@ -198,6 +248,22 @@ extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int 
       reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
       reinterpret_cast<__nv_bfloat16*>(out));
   MV_CHECK_LAUNCH("tokens_to_map");
+  return MV_OK;
+}
+
+extern "C" int mv_tokens_to_map_bwd(const void* dmap, void* dtokens, int64_t ldt, int batch, int n_tok, int prefix,
+                                    int grid, int target, int dim, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(dmap && dtokens && batch > 0, "mv_tokens_to_map_bwd: null/empty");
+  MV_CHECK_ARG(n_tok == prefix + grid * grid && dim % 8 == 0 && ldt % 8 == 0 && target <= 64, "mv_tokens_to_map_bwd: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const float inv_scale = (float)(1.0 / ((double)target / (double)grid));
+  int threads = dim / 8 < 256 ? (dim / 8 + 31) / 32 * 32 : 256;
+  if (threads < 2 * target) threads = (2 * target + 31) / 32 * 32;
+  tokens_to_map_bwd_kernel<<<batch * n_tok, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dmap), n_tok, prefix,
+                                                                 grid, target, dim, inv_scale,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dtokens), ldt);
+  MV_CHECK_LAUNCH("tokens_to_map_bwd");
   return MV_OK;
 }
 

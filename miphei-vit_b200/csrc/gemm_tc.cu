@@ -33,6 +33,7 @@ struct GemmDev {
   long long ldin2;
   int rows_per_group, group_stride, row_offset, resid_row_mod;
   // implicit-GEMM 3x3 convolution (pad 1) over NHWC sources: A tiles are TMA 4-D boxes, OOB zero fill = padding
+  int splits;          // split-K factor (MV_GEMM_NN_ATOMIC only, else 1)
   int conv;            // 0: A is a plain [M, K] matrix
   int conv_h, conv_w;  // OUTPUT spatial size
   int conv_tw;         // tile = conv_tw x (128 / conv_tw) output pixels (full rows when conv_w < 128)
@@ -172,8 +173,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  const int nkb = p.num_k_blocks;
+  const int num_mn = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = num_mn * p.splits;
+  const int nkb_total = p.num_k_blocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -181,8 +183,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
+        const int split = tile / num_mn, mn = tile - split * num_mn;
+        const int m_blk = mn % p.num_m_blocks;
+        const int n_blk = mn / p.num_m_blocks;
+        const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
         const int m0 = m_blk * GEMM_BLOCK_M;
         int brow[2];
         if (MODE == MV_GEMM_SWIGLU) {  // 128 gate rows + the matching 128 value rows
@@ -201,7 +205,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           cv_x = rem - cv_y * p.conv_w;
         }
         const int cbt = p.conv_cb0 + p.conv_cb1;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -217,8 +221,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
 #pragma unroll
+          if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
+            // B is [K, N] row-major: [64 k x 64 n] boxes, one per 64 output columns (MN-major UMMA operand)
+#pragma unroll
+            for (int ns = 0; ns < BLOCK_N / 64; ++ns)
+              tma_load_2d(sb + ns * 8192, &tmap_b, full_bar(stage), n_blk * BLOCK_N + ns * 64, kb * GEMM_BLOCK_K);
+          } else {
+#pragma unroll
           for (int bx = 0; bx < Cfg::kBoxesB; ++bx)
             tma_load_2d(sb + bx * (Cfg::kBoxRowsB * 128), &tmap_b, full_bar(stage), kb * GEMM_BLOCK_K, brow[bx]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -232,10 +244,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / num_mn;
+        const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -245,8 +259,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            if constexpr (MODE == MV_GEMM_HEAD_CONV) umma_bf16(d_tmem + kb * 16, da + 2 * k, db + 2 * k, idesc, k != 0);
-            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (MODE == MV_GEMM_HEAD_CONV) {
+              umma_bf16(d_tmem + kb * 16, da + 2 * k, db + 2 * k, idesc, k != 0);
+            } else if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
+              constexpr uint32_t idesc_mn = umma_idesc_bf16(GEMM_BLOCK_M, 64, 0, 1);
+#pragma unroll
+              for (int ns = 0; ns < BLOCK_N / 64; ++ns)
+                umma_bf16(d_tmem + ns * 64, da + 2 * k, umma_desc_sw128(sb + ns * 8192 + k * 2048, 1024, 1024), idesc_mn,
+                          (kb != kb0) || (k != 0));
+            } else {
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+            }
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -262,8 +285,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int mn = tile % num_mn;
+      const int m_blk = mn % p.num_m_blocks;
+      const int n_blk = mn / p.num_m_blocks;
       const int m = m_blk * GEMM_BLOCK_M + row_in_tile;
       const bool row_ok = m < p.m;
       mbar_wait(tfull_bar(as), aphase);
@@ -436,6 +460,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             stage_and_store(fv, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, half + j0);
           }
         }
+      } else if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
+        // split-K partial sums: fp32 reductions into the (pre-zeroed) output
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n_blk * BLOCK_N + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n_blk * BLOCK_N + c * 32 + j < p.n) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
+        }
       } else if constexpr (MODE == MV_GEMM_HEAD_GATE) {
         // columns = heads x 16 hidden units of AttentionBlock.psi: g_h = sigmoid(w2_h . relu(scale*acc+shift) + b2_h)
         const int heads = p.n / 16;
@@ -576,7 +614,8 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
     ta2 = ta;
   }
-  const CUtensorMap* tb = get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
+  const CUtensorMap* tb = MODE == MV_GEMM_NN_ATOMIC ? get_tmap_2d_bf16(a.b, a.k, a.n, a.ldb, 64)
+                                                    : get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
   if (!ta || !ta2 || !tb) return MV_ERR_ARG;
 
   GemmDev p;
@@ -590,6 +629,15 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.in2 = a.in2; p.ldin2 = a.ldin2;
   p.rows_per_group = a.rows_per_group; p.group_stride = a.group_stride; p.row_offset = a.row_offset;
   p.resid_row_mod = a.resid_row_mod;
+  p.splits = 1;
+  if (MODE == MV_GEMM_NN_ATOMIC) {
+    const int sms = device_sms() > 0 ? device_sms() : 148;
+    const int mn = p.num_m_blocks * p.num_n_blocks;
+    int sp = a.reserved_splits > 0 ? a.reserved_splits : (sms + mn - 1) / mn;
+    if (sp > p.num_k_blocks) sp = p.num_k_blocks;
+    if (sp < 1) sp = 1;
+    p.splits = sp;
+  }
   p.conv = a.conv;
   p.conv_h = a.conv_h; p.conv_w = a.conv_w;
   p.conv_tw = a.conv_w < 128 ? a.conv_w : 128;
@@ -597,7 +645,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.conv_cb0 = (a.conv_c0 + 63) / 64;
   p.conv_cb1 = (a.conv_c1 + 63) / 64;
 
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   int grid = device_sms() > 0 ? device_sms() : 148;
   if (tiles < grid) grid = tiles;
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
@@ -645,6 +693,9 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
     case MV_GEMM_SWIGLU_BWD:
       MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
       return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
+    case MV_GEMM_NN_ATOMIC:
+      MV_CHECK_ARG(!a.conv && a.out_f32 == 1 && a.n % 8 == 0, "mv_gemm_bf16(NN_ATOMIC): fp32 output, N %% 8 == 0");
+      return launch_gemm<128, MV_GEMM_NN_ATOMIC>(a, stream);
     case MV_GEMM_HEAD_CONV:
       MV_CHECK_ARG(a.conv && a.conv_c1 == 0 && a.conv_c0 <= 64 && a.conv_stride == 1 && a.n >= 1 && a.n <= 16 && a.shift &&
                        a.in2 && a.ldin2 >= a.n,

@@ -1,0 +1,99 @@
+// LoRA gradient path of QkvWithLoRA (src/generators/lora.py:16-18,29-33) for one transformer block.
+//
+// Forward (engine): T = xn [A_q | A_v]  (M x 16, stored in the 16 extension columns of the LayerNorm output) and the
+// QKV GEMM runs over K = D + 16 with the weight rows extended by alpha*B_q^T (q rows) / alpha*B_v^T (v rows).
+// Backward: dT = [dQ (alpha B_q)^T | dV (alpha B_v)^T] (16 extension columns of the dQKV buffer, produced by a skinny
+// tensor-core GEMM), and here
+//     dA_q = xn^T dT[:, 0:8]      dA_v = xn^T dT[:, 8:16]          (reduction over the M tokens)
+//     dB_q = alpha T[:, 0:8]^T dQ dB_v = alpha T[:, 8:16]^T dV
+// computed as two split-K tensor-core GEMMs (MV_GEMM_NN_ATOMIC) on the transposed skinny operands.
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+#include <string.h>
+
+namespace mv {
+
+// src0/src1: bf16 [M, 16] slices (row pitch ld0/ld1) -> dst0/dst1: bf16 [16, ldt] (row r = column r of the source)
+__global__ void transpose16_kernel(const __nv_bfloat16* __restrict__ src0, long long ld0,
+                                   const __nv_bfloat16* __restrict__ src1, long long ld1, __nv_bfloat16* __restrict__ dst0,
+                                   __nv_bfloat16* __restrict__ dst1, long long ldt, int M) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const __nv_bfloat16* s = blockIdx.y == 0 ? src0 : src1;
+  const long long ld = blockIdx.y == 0 ? ld0 : ld1;
+  __nv_bfloat16* d = blockIdx.y == 0 ? dst0 : dst1;
+  const uint4 a = *reinterpret_cast<const uint4*>(s + (long long)m * ld);
+  const uint4 b = *reinterpret_cast<const uint4*>(s + (long long)m * ld + 8);
+  const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    d[(long long)r * ldt + m] = pa[r];
+    d[(long long)(8 + r) * ldt + m] = pb[r];
+  }
+}
+
+// g_a: fp32 [16, D] = dAcat^T; g_b: fp32 [16, 3D] -> dA_q [D, 8], dA_v [D, 8], dB_q [8, D], dB_v [8, D]
+__global__ void lora_unpack_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, float* __restrict__ dAq,
+                                   float* __restrict__ dAv, float* __restrict__ dBq, float* __restrict__ dBv, int D,
+                                   float alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 8*D
+  if (i >= 8 * D) return;
+  const int r = i / D, d = i - r * D;
+  dAq[d * 8 + r] = g_a[(long long)r * D + d];
+  dAv[d * 8 + r] = g_a[(long long)(8 + r) * D + d];
+  dBq[(long long)r * D + d] = alpha * g_b[(long long)r * 3 * D + d];
+  dBv[(long long)r * D + d] = alpha * g_b[(long long)(8 + r) * 3 * D + 2 * D + d];
+}
+
+}  // namespace mv
+
+extern "C" int64_t mv_lora_grads_workspace_bytes(int m, int d) {
+  const int64_t ldt = (m + 7) / 8 * 8;
+  return 2 * 16 * ldt * 2 /*T^T, dT^T bf16*/ + 16ll * d * 4 + 16ll * 3 * d * 4 + 256;
+}
+
+// xn_ext bf16 [M, >= D+16] (LayerNorm output, T in columns D..D+15), dqkv_ext bf16 [M, >= 3D+16] (dT in columns
+// 3D..3D+15).  Outputs are written (not accumulated).
+extern "C" int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_ext, int64_t ldq, int m, int d, float alpha,
+                             float* dA_q, float* dA_v, float* dB_q, float* dB_v, void* workspace, int64_t workspace_bytes,
+                             void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(xn_ext && dqkv_ext && dA_q && dA_v && dB_q && dB_v && workspace && m > 0 && d > 0, "mv_lora_grads: null/empty");
+  MV_CHECK_ARG(workspace_bytes >= mv_lora_grads_workspace_bytes(m, d), "mv_lora_grads: workspace too small");
+  MV_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && ldx % 8 == 0 && ldq % 8 == 0 && d % 8 == 0,
+               "mv_lora_grads: alignment");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int64_t ldt = (m + 7) / 8 * 8;
+  __nv_bfloat16* tT = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* dtT = tT + 16 * ldt;
+  float* g_a = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((2 * 16 * ldt * 2 + 255) / 256) * 256);
+  float* g_b = g_a + 16ll * d;
+  const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(xn_ext);
+  const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(dqkv_ext);
+  dim3 grid((m + 255) / 256, 2);
+  transpose16_kernel<<<grid, 256, 0, stream>>>(xe + d, ldx, qe + 3ll * d, ldq, tT, dtT, ldt, m);
+  MV_CHECK_LAUNCH("transpose16");
+  cudaError_t e = cudaMemsetAsync(g_a, 0, (16ll * d + 16ll * 3 * d) * 4, stream);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  mv_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.mode = MV_GEMM_NN_ATOMIC;
+  a.out_f32 = 1;
+  a.m = 16;
+  a.k = m;
+  // dAcat^T [16, D] = dT^T [16, M] . xn [M, D]
+  a.a = dtT; a.lda = ldt; a.b = xn_ext; a.ldb = ldx; a.n = d; a.out = g_a; a.ldo = d;
+  int rc = mv_gemm_bf16(&a, stream_);
+  if (rc) return rc;
+  // dBcat [16, 3D] = T^T [16, M] . dQKV [M, 3D]
+  a.a = tT; a.b = dqkv_ext; a.ldb = ldq; a.n = 3 * d; a.out = g_b; a.ldo = 3 * d;
+  rc = mv_gemm_bf16(&a, stream_);
+  if (rc) return rc;
+  lora_unpack_kernel<<<(8 * d + 255) / 256, 256, 0, stream>>>(g_a, g_b, dA_q, dA_v, dB_q, dB_v, d, alpha);
+  MV_CHECK_LAUNCH("lora_unpack");
+  return MV_OK;
+}

@@ -34,6 +34,7 @@ class GemmArgs(ctypes.Structure):
         ("a2", c_void_p),
         ("conv_batch", c_i32), ("conv_h", c_i32), ("conv_w", c_i32), ("conv_stride", c_i32),
         ("conv_c0", c_i32), ("conv_c1", c_i32),
+        ("reserved_splits", c_i32), ("reserved2", c_i32),
     ]
 
 
@@ -55,6 +56,18 @@ _SIGNATURES = {
     "mv_fill_prefix": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_tokens_to_map": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_tokens_to_map_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_attn_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
+                            c_int, c_int, c_int, c_float, c_void_p]),
+    "mv_lora_grads_workspace_bytes": (c_i64, [c_int, c_int]),
+    "mv_lora_grads": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_i64, c_void_p]),
+    "mv_loss_workspace_floats": (c_i64, [c_int, c_int, c_int]),
+    "mv_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                c_void_p, c_void_p, c_i64, c_void_p]),
+    "mv_grad_norm": (c_int, [c_void_p, c_i64, c_float, c_void_p, c_void_p, c_void_p]),
+    "mv_adam_clip_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_float, c_float,
+                                  c_float, c_float, c_int, c_void_p]),
 }
 
 _lib = None

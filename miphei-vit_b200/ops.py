@@ -6,7 +6,7 @@ import torch
 
 from . import lib as _lib
 
-GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD, GEMM_HEAD_GATE, GEMM_HEAD_CONV = 0, 1, 2, 3, 4
+GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD, GEMM_HEAD_GATE, GEMM_HEAD_CONV, GEMM_NN_ATOMIC = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU = 0, 1
 
 
@@ -37,7 +37,10 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     lib = _lib_for(a)
     _rowmajor(b, "b")
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    N, Kb = b.shape
+    if mode == GEMM_NN_ATOMIC:
+        Kb, N = b.shape  # B is [K, N] row-major
+    else:
+        N, Kb = b.shape
     a2 = None
     if conv is not None:
         # a (and optionally conv["a2"]) are contiguous NHWC maps [B, Hin, Win, C]; conv = dict(stride=1|2, a2=None)
@@ -187,3 +190,85 @@ def upsample2x(x, out=None):
         out = torch.empty((B, 2 * h, 2 * w, C), dtype=torch.bfloat16, device=x.device)
     _lib.check(lib.mv_upsample2x(_ptr(x), _ptr(out), B, h, w, C, _stream()), "mv_upsample2x")
     return out
+
+
+def tokens_to_map_bwd(dmap, batch, n_tok, prefix, grid, out=None):
+    """adjoint of tokens_to_map: d_map NHWC bf16 -> d_tokens bf16 [B*n_tok, D] (mv_tokens_to_map_bwd)."""
+    lib = _lib_for(dmap)
+    assert dmap.dtype == torch.bfloat16 and dmap.is_contiguous()
+    B, t, _, D = dmap.shape
+    if out is None:
+        out = torch.empty((batch * n_tok, D), dtype=torch.bfloat16, device=dmap.device)
+    _lib.check(lib.mv_tokens_to_map_bwd(_ptr(dmap), _ptr(out), out.stride(0), batch, n_tok, prefix, grid, t, D, _stream()),
+               "mv_tokens_to_map_bwd")
+    return out
+
+
+def attn_bwd(qkv, out, dout, lse, batch, n_tok, heads, *, dqkv=None, dsum=None, scale=None):
+    """dq | dk | dv from dout and the saved forward tensors (mv_attn_bwd)."""
+    lib = _lib_for(qkv)
+    D = heads * 64
+    if dqkv is None:
+        dqkv = torch.empty((batch * n_tok, 3 * D), dtype=torch.bfloat16, device=qkv.device)
+    if dsum is None:
+        dsum = torch.empty((batch, heads, n_tok), dtype=torch.float32, device=qkv.device)
+    if scale is None:
+        scale = 64 ** -0.5
+    _lib.check(lib.mv_attn_bwd(_ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse),
+                               _ptr(dsum), _ptr(dqkv), dqkv.stride(0), batch, n_tok, heads, float(scale), _stream()),
+               "mv_attn_bwd")
+    return dqkv
+
+
+def lora_grads(xn_ext, dqkv_ext, D, alpha, dAq, dAv, dBq, dBv, workspace=None):
+    lib = _lib_for(xn_ext)
+    M = xn_ext.shape[0]
+    need = int(lib.mv_lora_grads_workspace_bytes(M, D))
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=xn_ext.device)
+    for t in (dAq, dAv, dBq, dBv):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _lib.check(lib.mv_lora_grads(_ptr(xn_ext), xn_ext.stride(0), _ptr(dqkv_ext), dqkv_ext.stride(0), M, D, float(alpha),
+                                 _ptr(dAq), _ptr(dAv), _ptr(dBq), _ptr(dBv), _ptr(workspace), workspace.numel(), _stream()),
+               "mv_lora_grads")
+    return workspace
+
+
+LOSS_WMSE, LOSS_MAE, LOSS_L1L2 = 0, 1, 2
+
+
+def loss_fwd_bwd(pred, target, weights=None, mode=LOSS_WMSE, lambda_factor=1.0, grad=None, want_grad=True,
+                 grad_scale=1.0, workspace=None, loss=None):
+    """loss (fp32 scalar tensor) and d loss / d pred in one pass (mv_loss_fwd_bwd); pred/target NCHW fp32."""
+    lib = _lib_for(pred)
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32 and pred.is_contiguous() and target.is_contiguous()
+    B, C, H, W = pred.shape
+    if want_grad and grad is None:
+        grad = torch.empty_like(pred)
+    nws = int(lib.mv_loss_workspace_floats(B, C, H * W))
+    if workspace is None:
+        workspace = torch.empty(nws, dtype=torch.float32, device=pred.device)
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    _lib.check(lib.mv_loss_fwd_bwd(_ptr(pred), _ptr(target), _ptr(grad if want_grad else None), _ptr(weights), B, C, H * W,
+                                   mode, float(lambda_factor), float(grad_scale), _ptr(loss), _ptr(workspace),
+                                   workspace.numel(), _stream()), "mv_loss_fwd_bwd")
+    return loss, grad
+
+
+def grad_norm(flat_grads, max_norm, norm_out=None, workspace=None):
+    lib = _lib_for(flat_grads)
+    if norm_out is None:
+        norm_out = torch.empty(2, dtype=torch.float32, device=flat_grads.device)
+    if workspace is None:
+        workspace = torch.empty(1024, dtype=torch.float32, device=flat_grads.device)
+    _lib.check(lib.mv_grad_norm(_ptr(flat_grads), flat_grads.numel(), float(max_norm), _ptr(norm_out), _ptr(workspace),
+                                _stream()), "mv_grad_norm")
+    return norm_out
+
+
+def adam_clip_step(params, grads, exp_avg, exp_avg_sq, norm_coef, step, lr, beta1=0.5, beta2=0.999, eps=1e-7, grad_mul=1.0):
+    lib = _lib_for(params)
+    _lib.check(lib.mv_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                     _ptr(norm_coef), float(grad_mul), float(lr), float(beta1), float(beta2), float(eps),
+                                     int(step), _stream()), "mv_adam_clip_step")
