@@ -62,7 +62,11 @@ class MipheiEngine:
         self._packed = False
         self._train_versions = None
         self._ws = {}
+        self._tapes = {}
         self.use_graphs = True
+        self._bwd_packed = False
+        self._lora_bwd_versions = None
+        self.on_encoder_backward_start = None  # trainer hook: decoder gradients are complete at this point
 
     # ------------------------------------------------------------------ geometry
     def _geometry(self):
@@ -84,6 +88,17 @@ class MipheiEngine:
         self._packed = False
         self._train_versions = None
         self._ws = {}
+        self._tapes = {}
+        self._bwd_packed = False
+        self._lora_bwd_versions = None
+
+    def _train_tape(self, B):
+        tape = self._tapes.get(B)
+        if tape is None:
+            from .autograd import _TrainTape
+            tape = _TrainTape(self, B)
+            self._tapes[B] = tape
+        return tape
 
     # ------------------------------------------------------------------ packing
     def _trainable_version(self):

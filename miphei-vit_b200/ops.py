@@ -121,12 +121,14 @@ def layernorm_fwd(x, w, b, *, out=None, eps=1e-6, stats=False):
     return (out, mean, rstd) if stats else out
 
 
-def layernorm_bwd(x, w, dy, *, dres=None, eps=1e-6, want_bf16=False):
+def layernorm_bwd(x, w, dy, *, dres=None, eps=1e-6, want_bf16=False, out=None, out_bf16=None):
     """dx = dres + dLN(dy) (mv_layernorm_bwd); returns fp32 dx (and a bf16 copy when want_bf16)."""
     lib = _lib_for(x)
     M, D = x.shape
-    dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
-    dxb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    dx = out if out is not None else torch.empty((M, D), dtype=torch.float32, device=x.device)
+    dxb = out_bf16 if out_bf16 is not None else (
+        torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None)
+    want_bf16 = dxb is not None
     _lib.check(lib.mv_layernorm_bwd(_ptr(x), x.stride(0), _ptr(w), _ptr(dy), dy.stride(0),
                                     1 if dy.dtype == torch.float32 else 0, _ptr(dres),
                                     dres.stride(0) if dres is not None else 0, _ptr(dx), dx.stride(0), _ptr(dxb),
@@ -134,14 +136,15 @@ def layernorm_bwd(x, w, dy, *, dres=None, eps=1e-6, want_bf16=False):
     return (dx, dxb) if want_bf16 else dx
 
 
-def attn_fwd(qkv, batch, n_tok, heads, *, out=None, want_lse=False, scale=None):
+def attn_fwd(qkv, batch, n_tok, heads, *, out=None, want_lse=False, scale=None, lse=None):
     """softmax(q k^T * scale) v per (image, head) from fused qkv rows (mv_attn_fwd)."""
     lib = _lib_for(qkv)
     _rowmajor(qkv, "qkv")
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (batch * n_tok, 3 * heads * 64)
     if out is None:
         out = torch.empty((batch * n_tok, heads * 64), dtype=torch.bfloat16, device=qkv.device)
-    lse = torch.empty((batch, heads, n_tok), dtype=torch.float32, device=qkv.device) if want_lse else None
+    if lse is None and want_lse:
+        lse = torch.empty((batch, heads, n_tok), dtype=torch.float32, device=qkv.device)
     if scale is None:
         scale = 64 ** -0.5
     _lib.check(lib.mv_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), _ptr(lse), batch, n_tok, heads,
