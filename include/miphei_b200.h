@@ -66,7 +66,11 @@ void mv_reset_launch_count(void);
  *                      ((p+0.9)/1.8).clamp(0,1)*255 truncated (src/callbacks.py:345-346).
  *   MV_GEMM_NN_ATOMIC  out[M, N] (fp32, caller-zeroed) += A[M, K] . B[K, N] with B ROW-major [K, N] (the reduction index is
  *                      the slow one: weight-gradient form, K = tokens / pixels), split-K across CTAs, fp32 atomics.
- *                      Used for the LoRA gradients dA = x^T dT, dB = (xA)^T dQ (src/generators/lora.py:16-18).
+ *                      Used for the LoRA gradients dA = x^T dT, dB = (xA)^T dQ (src/generators/lora.py:16-18) and, with
+ *                      conv = 1, for the 3x3 conv weight gradients: A = dz^T [Cout, pixels], B = the conv's NHWC input
+ *                      map(s) b (/ a2) read as tap-shifted TMA tiles; out[co, tap*Cpad + ci] in the packed weight layout.
+ *   MV_ACT_GATE_MASK   (LINEAR, bf16 out) out[m, n] = in2[m, n / 16] if acc*scale+shift > 0 else 0 — the ReLU-masked
+ *                      gradient of the heads' gate hidden units (AttentionBlock.psi backward).
  *
  * Implicit-GEMM 3x3 convolution (pad 1, stride 1|2; Basic_Conv3x3, src/generators/mipheivit.py:20-41): set conv = 1.
  * A is then read from one or two NHWC bf16 feature maps (channel concat: a = [B,Hin,Win,c0], a2 = [B,Hin,Win,c1],
@@ -75,7 +79,7 @@ void mv_reset_launch_count(void);
  * channels zero-padded to a multiple of 64, then the source-1 channels likewise.
  * ---------------------------------------------------------------------------------------------------------- */
 enum { MV_GEMM_LINEAR = 0, MV_GEMM_SWIGLU = 1, MV_GEMM_SWIGLU_BWD = 2, MV_GEMM_HEAD_GATE = 3, MV_GEMM_HEAD_CONV = 4, MV_GEMM_NN_ATOMIC = 5 };
-enum { MV_ACT_NONE = 0, MV_ACT_RELU = 1 };
+enum { MV_ACT_NONE = 0, MV_ACT_RELU = 1, MV_ACT_GATE_MASK = 2 };
 
 typedef struct mv_gemm_args {
   const void* a;      /* bf16 [M, K] */
@@ -104,6 +108,8 @@ typedef struct mv_gemm_args {
   int32_t conv_c0, conv_c1;
   int32_t reserved_splits; /* NN_ATOMIC: split-K factor, 0 = choose */
   int32_t reserved2;
+  float* colstats;    /* LINEAR + bf16 out: fp32 [2, N] += per-column (sum, sum of squares) of the stored values —
+                         BatchNorm batch statistics of a train-mode conv; out may be NULL (statistics only) */
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
@@ -186,6 +192,32 @@ int mv_grad_norm(const float* grads, int64_t n, float max_norm, float* norm_out,
 int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* norm_coef, float grad_mul, float lr, float beta1, float beta2, float eps, int step,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Train-mode BatchNorm2d + ReLU around the convs (Basic_Conv3x3, src/generators/mipheivit.py:20-41; AttentionBlock.psi[1],
+ * src/generators/unet.py:411-415); activations are NHWC bf16 seen as [M, C] rows.  See csrc/bn.cu.
+ *   mv_bn_finalize    (sum, sumsq) from the conv epilogue -> batch mean / rstd, folded (scale, shift), running-stat update
+ *                     (momentum, unbiased variance). pre_bias: bias added before the BN (psi[0].bias) or NULL.
+ *   mv_bn_relu_apply  y = relu(z*scale + shift)
+ *   mv_bn_relu_bwd    dz = BN'(dy * [y > 0]); sums (fp32 [2, C], overwritten) = (dbeta, dgamma)
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_bn_finalize(const float* colstats, double count, const float* gamma, const float* beta, const float* pre_bias,
+                   float* running_mean, float* running_var, float momentum, float eps, int c, float* scale, float* shift,
+                   float* mean, float* rstd, void* stream);
+int mv_bn_relu_apply(const void* z, const float* scale, const float* shift, void* y, int64_t m, int c, void* stream);
+int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, const float* mean, const float* rstd,
+                   const float* gamma, float* sums, void* dz, int64_t m, int c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Memory-bound kernels of the decoder backward pass (csrc/decoder_bwd_ew.cu).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row, void* stream);
+int mv_upsample2x_bwd(const void* dup, int64_t ldu, void* dx, int batch, int h, int w, int c, void* stream);
+int mv_zero_insert2x(const void* dz, void* u, int batch, int h, int w, int c, void* stream);
+int mv_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t m, int c, void* stream);
+int mv_heads_ds(const float* dpred, const float* pred, void* ds, float* dbias, int batch, int heads, int hw, void* stream);
+int mv_heads_bwd_stencil(const void* t, const void* ds, const void* gate, void* dt, void* du, float* db2, int batch, int h,
+                         int w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,316 @@
+// Memory-bound kernels of the decoder backward pass (NHWC bf16 feature maps).
+//
+//   mv_transpose_bf16       [M, C] -> [C(+ones row), M]: K-major copy of an activation / gradient for the weight-gradient
+//                           GEMMs (MV_GEMM_NN_ATOMIC needs the reduction index contiguous in A)
+//   mv_upsample2x_bwd       adjoint of Fusion_Block's bilinear x2 (mipheivit.py:89)
+//   mv_zero_insert2x        dgrad of a stride-2 conv = stride-1 conv over the zero-interleaved gradient
+//   mv_add_bf16             skip-connection gradient sums
+//   mv_heads_ds             ds = dpred * (1 - pred^2) (tanh'), NCHW fp32 -> NHWC bf16, and the head conv bias gradients
+//   mv_heads_bwd_stencil    gradients of the gated 3x3 head conv w.r.t. the gates and the per-tap projections
+//                           (SegmentationHead / AttentionBlock, src/generators/unet.py:407-438)
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+
+namespace mv {
+
+// in [M, C] (pitch ldi) -> out [R, ldo] with out[c, m] = in[m, c]; optional extra row C filled with ones.
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out,
+                                      long long ldo, long long M, int C, int ones_row) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const long long m = m0 + i;
+    const int c = c0 + threadIdx.x * 2;
+    __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
+    if (m < M && c < C) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(in + m * ldi + c);
+      a = v.x; b = v.y;
+    }
+    tile[i][threadIdx.x * 2] = a;
+    tile[i][threadIdx.x * 2 + 1] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long m = m0 + threadIdx.x * 2;
+    if (c < C && m < M) {
+      __nv_bfloat162 v;
+      v.x = tile[threadIdx.x * 2][i];
+      v.y = tile[threadIdx.x * 2 + 1][i];
+      if (m + 1 < M) *reinterpret_cast<__nv_bfloat162*>(out + (long long)c * ldo + m) = v;
+      else out[(long long)c * ldo + m] = v.x;
+    }
+  }
+  if (ones_row && blockIdx.y == 0) {
+    const __nv_bfloat16 one = __float2bfloat16(1.f);
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < 64; i += 32 * blockDim.y)
+      if (m0 + i < M) out[(long long)C * ldo + m0 + i] = one;
+  }
+}
+
+// dup [B, 2h, 2w, C] (pitch ldu per pixel) -> dx [B, h, w, C]; one thread per (input pixel, 8 channels)
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dup, long long ldu, __nv_bfloat16* __restrict__ dx,
+                                      int B, int h, int w, int C) {
+  const int cg = C / 8;
+  const long long total = (long long)B * h * w * cg;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cg);
+  long long r = i / cg;
+  const int x = (int)(r % w);
+  r /= w;
+  const int y = (int)(r % h);
+  const long long b = r / h;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int oy = max(2 * y - 2, 0); oy <= min(2 * y + 2, 2 * h - 1); ++oy) {
+    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
+    const float ly = sy - y0;
+    const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = max(2 * x - 2, 0); ox <= min(2 * x + 2, 2 * w - 1); ++ox) {
+      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
+      const float lx = sx - x0;
+      const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+      if (wx == 0.f) continue;
+      const float wgt = wy * wx;
+      const uint4 u = *reinterpret_cast<const uint4*>(dup + ((b * 2 * h + oy) * 2 * w + ox) * ldu + c8 * 8);
+      const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+      acc[0] += wgt * p0.x; acc[1] += wgt * p0.y; acc[2] += wgt * p1.x; acc[3] += wgt * p1.y;
+      acc[4] += wgt * p2.x; acc[5] += wgt * p2.y; acc[6] += wgt * p3.x; acc[7] += wgt * p3.y;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]);
+  o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]);
+  o.w = pack_bf16x2(acc[6], acc[7]);
+  reinterpret_cast<uint4*>(dx)[i] = o;
+}
+
+// u [B, 2h, 2w, C]: u[2y, 2x] = dz[y, x], zero elsewhere
+__global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ u, int B, int h,
+                                     int w, int C) {
+  const int cg = C / 8;
+  const long long total = (long long)B * 4 * h * w * cg;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cg);
+  long long r = i / cg;
+  const int ox = (int)(r % (2 * w));
+  r /= (2 * w);
+  const int oy = (int)(r % (2 * h));
+  const long long b = r / (2 * h);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (!(ox & 1) && !(oy & 1)) v = reinterpret_cast<const uint4*>(dz)[((b * h + oy / 2) * w + ox / 2) * cg + c8];
+  reinterpret_cast<uint4*>(u)[i] = v;
+}
+
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
+                                long long ldb, __nv_bfloat16* __restrict__ out, long long M, int C) {
+  const int cg = C / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * cg) return;
+  const int c = (int)(i % cg) * 8;
+  const long long r = i / cg;
+  const uint4 ua = *reinterpret_cast<const uint4*>(a + r * lda + c);
+  const uint4 ub = *reinterpret_cast<const uint4*>(b + r * ldb + c);
+  const uint32_t* pa = &ua.x; const uint32_t* pb = &ub.x;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = unpack_bf16x2(pa[j]), fb = unpack_bf16x2(pb[j]);
+    o[j] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ds[p, h] = dpred[b, h, p] * (1 - pred[b, h, p]^2); dbias[h] += sum_p ds. grid = (pixel blocks, B); block = 256 pixels
+__global__ void __launch_bounds__(256) heads_ds_kernel(const float* __restrict__ dpred, const float* __restrict__ pred,
+                                                       __nv_bfloat16* __restrict__ ds, float* __restrict__ dbias, int heads,
+                                                       int hw) {
+  __shared__ float sh[8];
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = p < hw;
+  float vals[16];
+  for (int h = 0; h < heads; ++h) {
+    float v = 0.f;
+    if (ok) {
+      const long long i = ((long long)b * heads + h) * hw + p;
+      const float y = pred[i];
+      v = dpred[i] * (1.f - y * y);
+    }
+    vals[h] = v;
+    float s = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int wv = 0; wv < 8; ++wv) t += sh[wv];
+      atomicAdd(dbias + h, t);
+    }
+    __syncthreads();
+  }
+  if (ok) {
+    __nv_bfloat16* o = ds + ((long long)b * hw + p) * 16;
+    uint32_t u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(2 * j < heads ? vals[2 * j] : 0.f, 2 * j + 1 < heads ? vals[2 * j + 1] : 0.f);
+    reinterpret_cast<uint4*>(o)[0] = make_uint4(u[0], u[1], u[2], u[3]);
+    reinterpret_cast<uint4*>(o)[1] = make_uint4(u[4], u[5], u[6], u[7]);
+  }
+}
+
+// per pixel p' (thread): for tap = (ky, kx): n = ds[p' - (ky-1, kx-1)] (zero outside the image)
+//   dt[p', tap*16 + h] = g[p', h] * n[h];   dg[h] += n[h] * t[p', tap*16 + h];   du[h] = dg[h] * g (1 - g)
+// t, dt: bf16 [M, 144]; ds, gate: bf16 [M, 16]; du: bf16 [M, 16]; db2[h] += sum_p du
+__global__ void __launch_bounds__(128) heads_bwd_stencil_kernel(const __nv_bfloat16* __restrict__ t,
+                                                                const __nv_bfloat16* __restrict__ ds,
+                                                                const __nv_bfloat16* __restrict__ gate,
+                                                                __nv_bfloat16* __restrict__ dt,
+                                                                __nv_bfloat16* __restrict__ du, float* __restrict__ db2,
+                                                                int H, int W, long long M) {
+  __shared__ float sh[4][16];
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = m < M;
+  float dg[16], g[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { dg[j] = 0.f; g[j] = 0.f; }
+  if (ok) {
+    const long long hw = (long long)H * W;
+    const long long b = m / hw;
+    const int rem = (int)(m - b * hw);
+    const int py = rem / W, px = rem - py * W;
+    {
+      const uint4 a = reinterpret_cast<const uint4*>(gate + m * 16)[0], c = reinterpret_cast<const uint4*>(gate + m * 16)[1];
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(u[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+    }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+      float n[16];
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const __nv_bfloat16* q = ds + (b * hw + (long long)yy * W + xx) * 16;
+        const uint4 a = reinterpret_cast<const uint4*>(q)[0], c = reinterpret_cast<const uint4*>(q)[1];
+        const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(u[j]); n[2 * j] = f.x; n[2 * j + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) n[j] = 0.f;
+      }
+      const __nv_bfloat16* tp = t + m * 144 + tap * 16;
+      const uint4 a = reinterpret_cast<const uint4*>(tp)[0], c = reinterpret_cast<const uint4*>(tp)[1];
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        dg[2 * j] += n[2 * j] * f.x;
+        dg[2 * j + 1] += n[2 * j + 1] * f.y;
+        o[j] = pack_bf16x2(g[2 * j] * n[2 * j], g[2 * j + 1] * n[2 * j + 1]);
+      }
+      __nv_bfloat16* op = dt + m * 144 + tap * 16;
+      reinterpret_cast<uint4*>(op)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<uint4*>(op)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  float duv[16];
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) duv[j] = dg[j] * g[j] * (1.f - g[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(duv[2 * j], duv[2 * j + 1]);
+  if (ok) {
+    reinterpret_cast<uint4*>(du + m * 16)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(du + m * 16)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float s = warp_sum(duv[j]);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) atomicAdd(db2 + threadIdx.x, sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+
+}  // namespace mv
+
+extern "C" int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row,
+                                 void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(in && out && m > 0 && c > 0 && c % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0 && ldo >= m, "mv_transpose_bf16: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid((unsigned)((m + 63) / 64), (c + 63) / 64), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldi,
+                                                    reinterpret_cast<__nv_bfloat16*>(out), ldo, m, c, ones_row);
+  MV_CHECK_LAUNCH("transpose_bf16");
+  return MV_OK;
+}
+
+extern "C" int mv_upsample2x_bwd(const void* dup, int64_t ldu, void* dx, int batch, int h, int w, int c, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(dup && dx && batch > 0 && c % 8 == 0 && ldu % 8 == 0, "mv_upsample2x_bwd: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = (long long)batch * h * w * (c / 8);
+  upsample2x_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dup), ldu, reinterpret_cast<__nv_bfloat16*>(dx), batch, h, w, c);
+  MV_CHECK_LAUNCH("upsample2x_bwd");
+  return MV_OK;
+}
+
+extern "C" int mv_zero_insert2x(const void* dz, void* u, int batch, int h, int w, int c, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(dz && u && batch > 0 && c % 8 == 0, "mv_zero_insert2x: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = (long long)batch * 4 * h * w * (c / 8);
+  zero_insert2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<__nv_bfloat16*>(u), batch, h, w, c);
+  MV_CHECK_LAUNCH("zero_insert2x");
+  return MV_OK;
+}
+
+extern "C" int mv_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t m, int c,
+                           void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(a && b && out && m > 0 && c % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "mv_add_bf16: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = m * (c / 8);
+  add_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), lda, reinterpret_cast<const __nv_bfloat16*>(b), ldb,
+      reinterpret_cast<__nv_bfloat16*>(out), m, c);
+  MV_CHECK_LAUNCH("add_bf16");
+  return MV_OK;
+}
+
+// dpred / pred: NCHW fp32 [B, heads, H*W]; ds: bf16 [B*H*W, 16] (columns >= heads zero); dbias fp32 [heads] (+=)
+extern "C" int mv_heads_ds(const float* dpred, const float* pred, void* ds, float* dbias, int batch, int heads, int hw,
+                           void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(dpred && pred && ds && dbias && batch > 0 && heads >= 1 && heads <= 16, "mv_heads_ds: shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid((hw + 255) / 256, batch);
+  heads_ds_kernel<<<grid, 256, 0, stream>>>(dpred, pred, reinterpret_cast<__nv_bfloat16*>(ds), dbias, heads, hw);
+  MV_CHECK_LAUNCH("heads_ds");
+  return MV_OK;
+}
+
+extern "C" int mv_heads_bwd_stencil(const void* t, const void* ds, const void* gate, void* dt, void* du, float* db2,
+                                    int batch, int h, int w, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(t && ds && gate && dt && du && db2 && batch > 0, "mv_heads_bwd_stencil: null/empty");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long M = (long long)batch * h * w;
+  heads_bwd_stencil_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(t), reinterpret_cast<const __nv_bfloat16*>(ds),
+      reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(dt),
+      reinterpret_cast<__nv_bfloat16*>(du), db2, h, w, M);
+  MV_CHECK_LAUNCH("heads_bwd_stencil");
+  return MV_OK;
+}

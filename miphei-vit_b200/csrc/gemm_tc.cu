@@ -33,6 +33,7 @@ struct GemmDev {
   long long ldin2;
   int rows_per_group, group_stride, row_offset, resid_row_mod;
   // implicit-GEMM 3x3 convolution (pad 1) over NHWC sources: A tiles are TMA 4-D boxes, OOB zero fill = padding
+  float* colstats;     // optional fp32 [2, N]: per-column sum and sum of squares of the stored values (atomic)
   int splits;          // split-K factor (MV_GEMM_NN_ATOMIC only, else 1)
   int conv;            // 0: A is a plain [M, K] matrix
   int conv_h, conv_w;  // OUTPUT spatial size
@@ -197,7 +198,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           brow[1] = n_blk * BLOCK_N + 128;
         }
         int cv_b = 0, cv_y = 0, cv_x = 0;
-        if (p.conv) {  // tile rows are contiguous output pixels: m0 -> (image, y0, x0)
+        if (p.conv && MODE != MV_GEMM_NN_ATOMIC) {  // tile rows are contiguous output pixels: m0 -> (image, y0, x0)
           const int hw = p.conv_h * p.conv_w;
           cv_b = m0 / hw;
           const int rem = m0 - cv_b * hw;
@@ -209,8 +210,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if (p.conv) {
+          const bool nn_conv = MODE == MV_GEMM_NN_ATOMIC && p.conv;
+          if (!nn_conv) mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (nn_conv) {
+          } else if (p.conv) {
             const int tap = kb / cbt;
             const int cbi = kb - tap * cbt;
             const int ky = tap / 3, kx = tap - ky * 3;
@@ -223,9 +226,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
             // B is [K, N] row-major: [64 k x 64 n] boxes, one per 64 output columns (MN-major UMMA operand)
+            if (p.conv) {
+              // weight gradient of a 3x3 conv: k = output pixel, n = (tap, input channel); the B box is the input map
+              // shifted by the tap (TMA 4-D tile of 64 pixels x 64 channels, zero fill = padding)
+              const int hw = p.conv_h * p.conv_w;
+              const int pm0 = kb * GEMM_BLOCK_K;
+              const int pb = pm0 / hw, prem = pm0 - pb * hw;
+              const int py0 = prem / p.conv_w, px0 = prem - py0 * p.conv_w;
+              int nvalid = 0;
+#pragma unroll
+              for (int ns = 0; ns < BLOCK_N / 64; ++ns) nvalid += (n_blk * (BLOCK_N / 64) + ns) < 9 * cbt ? 1 : 0;
+              mbar_expect_tx(full_bar(stage), Cfg::kABytes + nvalid * 8192);
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
+#pragma unroll
+              for (int ns = 0; ns < BLOCK_N / 64; ++ns) {
+                const int nb = n_blk * (BLOCK_N / 64) + ns;
+                if (nb < 9 * cbt) {
+                  const int tap = nb / cbt, cbi = nb - tap * cbt;
+                  const int ky = tap / 3, kx = tap - ky * 3;
+                  const int ix = px0 * p.conv_stride + kx - 1, iy = py0 * p.conv_stride + ky - 1;
+                  if (cbi < p.conv_cb0) tma_load_4d(sb + ns * 8192, &tmap_b, full_bar(stage), cbi * 64, ix, iy, pb);
+                  else tma_load_4d(sb + ns * 8192, &tmap_a2, full_bar(stage), (cbi - p.conv_cb0) * 64, ix, iy, pb);
+                }
+              }
+            } else {
 #pragma unroll
             for (int ns = 0; ns < BLOCK_N / 64; ++ns)
               tma_load_2d(sb + ns * 8192, &tmap_b, full_bar(stage), n_blk * BLOCK_N + ns * 64, kb * GEMM_BLOCK_K);
+            }
           } else {
 #pragma unroll
           for (int bx = 0; bx < Cfg::kBoxesB; ++bx)
@@ -357,43 +385,72 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             const int col = (lane & 3) * 8;
             const int nn = n0 + col;
-            if (nn < p.n) {
-              float sc[8], sh[8];
+            const bool col_ok = nn < p.n;
+            float sc[8], sh[8], csum[8], csq[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
-              if (p.scale) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + nn + 4));
-                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-              }
-              if (p.shift) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + nn + 4));
-                sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-              }
+            for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; csum[j] = 0.f; csq[j] = 0.f; }
+            if (p.scale && col_ok) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + nn + 4));
+              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            }
+            if (p.shift && col_ok) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + nn + 4));
+              sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+            }
 #pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int r = it * 8 + (lane >> 2);
-                const int mm = m_warp + r;
-                if (mm < p.m) {
-                  const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 36 + col);
-                  const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 36 + col + 4);
-                  float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2);
+              const int mm = m_warp + r;
+              if (mm < p.m && col_ok) {
+                const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+                const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 36 + col + 4);
+                float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[j] = f[j] * sc[j] + sh[j];
+                  if (p.act == MV_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.act == MV_ACT_GATE_MASK) {  // e = du[m, head] where the (batch-normalised) unit is active
+                  const float du = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nn >> 4)]);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? du : 0.f;
+                }
+                long long orow = mm, rrow = mm;
+                if (p.rows_per_group > 0) {
+                  const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
+                  orow = (long long)g * p.group_stride + rr + p.row_offset;
+                  rrow = p.resid_row_mod ? rr : orow;
+                }
+                if (p.resid) {
+                  const float* q = p.resid + rrow * p.ldr + nn;
+                  const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+                  f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w; f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
+                }
+                if (p.colstats) {  // BatchNorm batch statistics of exactly what is stored (bf16-rounded)
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
-                    f[j] = f[j] * sc[j] + sh[j];
-                    if (p.act == MV_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+                    const float fr = __bfloat162float(__float2bfloat16(f[j]));
+                    csum[j] += fr;
+                    csq[j] += fr * fr;
                   }
-                  long long orow = mm, rrow = mm;
-                  if (p.rows_per_group > 0) {
-                    const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
-                    orow = (long long)g * p.group_stride + rr + p.row_offset;
-                    rrow = p.resid_row_mod ? rr : orow;
-                  }
-                  if (p.resid) {
-                    const float* q = p.resid + rrow * p.ldr + nn;
-                    const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
-                    f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w; f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
-                  }
-                  store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nn, f);
+                }
+                if (p.out) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nn, f);
+              }
+            }
+            if (p.colstats) {  // rows live in lane >> 2: fold the 8 row groups, then one atomic per column per warp
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                  csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], o);
+                  csq[j] += __shfl_xor_sync(0xffffffffu, csq[j], o);
+                }
+              }
+              if (lane < 4 && col_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  atomicAdd(p.colstats + nn + j, csum[j]);
+                  atomicAdd(p.colstats + p.n + nn + j, csq[j]);
                 }
               }
             }
@@ -602,7 +659,18 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   }
   const CUtensorMap* ta = nullptr;
   const CUtensorMap* ta2 = nullptr;
-  if (a.conv) {
+  const CUtensorMap* tb_conv = nullptr;
+  if (a.conv && MODE == MV_GEMM_NN_ATOMIC) {
+    const int tw = a.conv_w < 64 ? a.conv_w : 64;
+    const int th = 64 / tw;
+    ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
+    tb_conv = get_tmap_nhwc_bf16(a.b, a.conv_batch, a.conv_h * a.conv_stride, a.conv_w * a.conv_stride, a.conv_c0, tw, th,
+                                 a.conv_stride);
+    ta2 = a.conv_c1 > 0 ? get_tmap_nhwc_bf16(a.a2, a.conv_batch, a.conv_h * a.conv_stride, a.conv_w * a.conv_stride,
+                                             a.conv_c1, tw, th, a.conv_stride)
+                        : tb_conv;
+    if (!tb_conv) return MV_ERR_ARG;
+  } else if (a.conv) {
     const int tw = a.conv_w < 128 ? a.conv_w : 128;
     const int th = 128 / tw;
     ta = get_tmap_nhwc_bf16(a.a, a.conv_batch, a.conv_h * a.conv_stride, a.conv_w * a.conv_stride, a.conv_c0, tw, th,
@@ -614,8 +682,9 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
     ta2 = ta;
   }
-  const CUtensorMap* tb = MODE == MV_GEMM_NN_ATOMIC ? get_tmap_2d_bf16(a.b, a.k, a.n, a.ldb, 64)
-                                                    : get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
+  const CUtensorMap* tb = tb_conv ? tb_conv
+                          : MODE == MV_GEMM_NN_ATOMIC ? get_tmap_2d_bf16(a.b, a.k, a.n, a.ldb, 64)
+                                                      : get_tmap_2d_bf16(a.b, a.n, a.k, a.ldb, Cfg::kBoxRowsB);
   if (!ta || !ta2 || !tb) return MV_ERR_ARG;
 
   GemmDev p;
@@ -630,6 +699,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.rows_per_group = a.rows_per_group; p.group_stride = a.group_stride; p.row_offset = a.row_offset;
   p.resid_row_mod = a.resid_row_mod;
   p.splits = 1;
+  p.colstats = a.colstats;
   if (MODE == MV_GEMM_NN_ATOMIC) {
     const int sms = device_sms() > 0 ? device_sms() : 148;
     const int mn = p.num_m_blocks * p.num_n_blocks;
@@ -660,12 +730,21 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   MV_CHECK_ARG(args != nullptr, "mv_gemm_bf16: null args");
   const mv_gemm_args& a = *args;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MV_CHECK_ARG(a.a && a.b && a.out, "mv_gemm_bf16: null operand");
+  MV_CHECK_ARG(a.a && a.b && (a.out || a.colstats), "mv_gemm_bf16: null operand");
+  MV_CHECK_ARG(!a.colstats || (a.mode == MV_GEMM_LINEAR && !a.out_f32 && a.n >= 32), "mv_gemm_bf16: colstats needs LINEAR mode, bf16 output, N >= 32");
   MV_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0, "mv_gemm_bf16: empty problem m=%d n=%d k=%d", a.m, a.n, a.k);
   MV_CHECK_ARG(a.n % 8 == 0 || a.mode == MV_GEMM_HEAD_CONV, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
   MV_CHECK_ARG(a.k % 8 == 0 || a.mode == MV_GEMM_NN_ATOMIC, "mv_gemm_bf16: K=%d must be a multiple of 8", a.k);
   MV_CHECK_ARG((a.conv || a.lda % 8 == 0) && a.ldb % 8 == 0, "mv_gemm_bf16: lda/ldb must be multiples of 8 elements");
-  if (a.conv) {
+  if (a.conv && a.mode == MV_GEMM_NN_ATOMIC) {
+    MV_CHECK_ARG(a.conv_stride == 1 || a.conv_stride == 2, "mv_gemm_bf16: conv stride must be 1 or 2");
+    MV_CHECK_ARG(a.conv_c0 > 0 && a.conv_c0 % 8 == 0 && a.conv_c1 % 8 == 0 && (a.conv_c1 == 0 || a.a2),
+                 "mv_gemm_bf16: conv channel counts must be multiples of 8");
+    MV_CHECK_ARG(a.conv_w > 0 && a.conv_h > 0 && (a.conv_w % 64 == 0 || 64 % a.conv_w == 0) && (a.conv_h * a.conv_w) % 64 == 0,
+                 "mv_gemm_bf16: wgrad output map %dx%d must tile into 64-pixel row blocks", a.conv_h, a.conv_w);
+    MV_CHECK_ARG(a.k == a.conv_batch * a.conv_h * a.conv_w, "mv_gemm_bf16: wgrad K must be batch*H*W");
+    MV_CHECK_ARG(a.n == 9 * 64 * ((a.conv_c0 + 63) / 64 + (a.conv_c1 + 63) / 64), "mv_gemm_bf16: wgrad N must be 9 x padded channels");
+  } else if (a.conv) {
     MV_CHECK_ARG(a.mode == MV_GEMM_LINEAR || a.mode == MV_GEMM_HEAD_CONV,
                  "mv_gemm_bf16: conv A operand only with MV_GEMM_LINEAR / MV_GEMM_HEAD_CONV");
     MV_CHECK_ARG(a.conv_stride == 1 || a.conv_stride == 2, "mv_gemm_bf16: conv stride must be 1 or 2");
@@ -694,7 +773,7 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
       MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
       return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
     case MV_GEMM_NN_ATOMIC:
-      MV_CHECK_ARG(!a.conv && a.out_f32 == 1 && a.n % 8 == 0, "mv_gemm_bf16(NN_ATOMIC): fp32 output, N %% 8 == 0");
+      MV_CHECK_ARG(a.out_f32 == 1 && a.n % 8 == 0, "mv_gemm_bf16(NN_ATOMIC): fp32 output, N %% 8 == 0");
       return launch_gemm<128, MV_GEMM_NN_ATOMIC>(a, stream);
     case MV_GEMM_HEAD_CONV:
       MV_CHECK_ARG(a.conv && a.conv_c1 == 0 && a.conv_c0 <= 64 && a.conv_stride == 1 && a.n >= 1 && a.n <= 16 && a.shift &&

@@ -35,6 +35,7 @@ class GemmArgs(ctypes.Structure):
         ("conv_batch", c_i32), ("conv_h", c_i32), ("conv_w", c_i32), ("conv_stride", c_i32),
         ("conv_c0", c_i32), ("conv_c1", c_i32),
         ("reserved_splits", c_i32), ("reserved2", c_i32),
+        ("colstats", c_void_p),
     ]
 
 
@@ -62,6 +63,18 @@ _SIGNATURES = {
     "mv_lora_grads_workspace_bytes": (c_i64, [c_int, c_int]),
     "mv_lora_grads": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_i64, c_void_p]),
+    "mv_bn_finalize": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                               c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv_bn_relu_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mv_bn_relu_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                               c_int, c_void_p]),
+    "mv_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
+    "mv_upsample2x_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_zero_insert2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_add_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p]),
+    "mv_heads_ds": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv_heads_bwd_stencil": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_void_p]),
     "mv_loss_workspace_floats": (c_i64, [c_int, c_int, c_int]),
     "mv_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                 c_void_p, c_void_p, c_i64, c_void_p]),

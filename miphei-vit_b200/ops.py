@@ -7,7 +7,7 @@ import torch
 from . import lib as _lib
 
 GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD, GEMM_HEAD_GATE, GEMM_HEAD_CONV, GEMM_NN_ATOMIC = 0, 1, 2, 3, 4, 5
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_GATE_MASK = 0, 1, 2
 
 
 def _stream():
@@ -32,17 +32,31 @@ def _rowmajor(t, name):
 
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
-         resid_row_mod=False, block_n=0, conv=None, out_kind=None):
+         resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
     lib = _lib_for(a)
-    _rowmajor(b, "b")
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    if mode == GEMM_NN_ATOMIC:
+    if mode == GEMM_NN_ATOMIC and conv is not None:
+        N = Kb = None
+    elif mode == GEMM_NN_ATOMIC:
+        _rowmajor(b, "b")
         Kb, N = b.shape  # B is [K, N] row-major
     else:
+        _rowmajor(b, "b")
         N, Kb = b.shape
     a2 = None
-    if conv is not None:
+    if conv is not None and mode == GEMM_NN_ATOMIC:
+        # weight gradient: a = dz^T [Cout, pixels]; b (and conv["a2"]) = NHWC input maps of the conv
+        stride = conv.get("stride", 1)
+        a2 = conv.get("a2")
+        _rowmajor(a, "a")
+        assert b.dim() == 4 and b.is_contiguous()
+        Bc, Hin, Win, C0 = b.shape
+        C1 = a2.shape[3] if a2 is not None else 0
+        Ho, Wo = Hin // stride, Win // stride
+        M, K = a.shape
+        N, Kb = 9 * 64 * ((C0 + 63) // 64 + (C1 + 63) // 64), Bc * Ho * Wo
+    elif conv is not None:
         # a (and optionally conv["a2"]) are contiguous NHWC maps [B, Hin, Win, C]; conv = dict(stride=1|2, a2=None)
         stride = conv.get("stride", 1)
         a2 = conv.get("a2")
@@ -63,7 +77,9 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
         out_cols = N
     if mode == GEMM_HEAD_GATE:
         out_cols = N // 16
-    if mode == GEMM_HEAD_CONV:
+    if no_out:
+        assert colstats is not None and out is None
+    elif mode == GEMM_HEAD_CONV:
         if out is None:
             out = torch.empty((Bc, N, Ho, Wo), dtype=out_dtype, device=a.device)
         assert out.is_contiguous()
@@ -72,17 +88,23 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
             out = torch.empty((out_rows if out_rows is not None else M, out_cols), dtype=out_dtype, device=a.device)
         _rowmajor(out, "out")
     args = _lib.GemmArgs()
-    args.a, args.lda = a.data_ptr(), (a.stride(0) if conv is None else 0)
+    args.a, args.lda = a.data_ptr(), (a.stride(0) if a.dim() == 2 else 0)
     if conv is not None:
         args.conv = 1
         args.a2 = a2.data_ptr() if a2 is not None else None
         args.conv_batch, args.conv_h, args.conv_w, args.conv_stride = Bc, Ho, Wo, stride
         args.conv_c0, args.conv_c1 = C0, C1
-    args.b, args.ldb = b.data_ptr(), b.stride(0)
+    args.b, args.ldb = b.data_ptr(), (b.stride(0) if b.dim() == 2 else 0)
     args.m, args.n, args.k = M, N, K
     args.mode, args.act = mode, act
-    args.out_f32 = 1 if out.dtype == torch.float32 else (2 if out.dtype == torch.uint8 else 0)
-    args.out, args.ldo = out.data_ptr(), (out.stride(0) if mode != GEMM_HEAD_CONV else 0)
+    if colstats is not None:
+        assert colstats.dtype == torch.float32 and colstats.is_contiguous() and colstats.numel() == 2 * N
+        args.colstats = colstats.data_ptr()
+    if no_out:
+        args.out_f32, args.out, args.ldo = 0, None, 0
+    else:
+        args.out_f32 = 1 if out.dtype == torch.float32 else (2 if out.dtype == torch.uint8 else 0)
+        args.out, args.ldo = out.data_ptr(), (out.stride(0) if mode != GEMM_HEAD_CONV else 0)
     if aux is not None:
         args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
     if scale is not None:
@@ -275,3 +297,108 @@ def adam_clip_step(params, grads, exp_avg, exp_avg_sq, norm_coef, step, lr, beta
     _lib.check(lib.mv_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
                                      _ptr(norm_coef), float(grad_mul), float(lr), float(beta1), float(beta2), float(eps),
                                      int(step), _stream()), "mv_adam_clip_step")
+
+
+def bn_finalize(colstats, count, gamma, beta, running_mean, running_var, pre_bias=None, momentum=0.1, eps=1e-5, out=None):
+    """batch statistics -> (scale, shift, mean, rstd) + running-stat update (mv_bn_finalize)."""
+    lib = _lib_for(colstats)
+    C = gamma.numel()
+    if out is None:
+        out = torch.empty((4, C), dtype=torch.float32, device=colstats.device)
+    _lib.check(lib.mv_bn_finalize(_ptr(colstats), float(count), _ptr(gamma), _ptr(beta), _ptr(pre_bias), _ptr(running_mean),
+                                  _ptr(running_var), float(momentum), float(eps), C, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                  _ptr(out[3]), _stream()), "mv_bn_finalize")
+    return out
+
+
+def bn_relu_apply(z, scale, shift, out=None):
+    lib = _lib_for(z)
+    M, C = z.shape
+    assert z.is_contiguous()
+    if out is None:
+        out = torch.empty_like(z)
+    _lib.check(lib.mv_bn_relu_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(out), M, C, _stream()), "mv_bn_relu_apply")
+    return out
+
+
+def bn_relu_bwd(dy, y, z, mean, rstd, gamma, sums=None, dz=None):
+    """dz = BN'(dy * [y>0]); returns (dz, sums) with sums[0] = dbeta, sums[1] = dgamma (mv_bn_relu_bwd)."""
+    lib = _lib_for(dy)
+    M, C = z.shape
+    assert y.is_contiguous() and z.is_contiguous() and dy.stride(1) == 1
+    if sums is None:
+        sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    if dz is None:
+        dz = torch.empty_like(z)
+    _lib.check(lib.mv_bn_relu_bwd(_ptr(dy), dy.stride(0), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums),
+                                  _ptr(dz), M, C, _stream()), "mv_bn_relu_bwd")
+    return dz, sums
+
+
+def transpose_bf16(x, ones_row=False, out=None):
+    """[M, C] (strided rows) -> [C (+1 ones row, padded to 8 rows), ld >= M] K-major copy (mv_transpose_bf16)."""
+    lib = _lib_for(x)
+    M, C = x.shape
+    ld = (M + 7) // 8 * 8
+    rows = C + (8 if ones_row else 0)
+    if out is None:
+        out = torch.zeros((rows, ld), dtype=torch.bfloat16, device=x.device) if ones_row else \
+            torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.mv_transpose_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, C, 1 if ones_row else 0, _stream()),
+               "mv_transpose_bf16")
+    return out
+
+
+def upsample2x_bwd(dup, out=None):
+    """dup: [B, 2h, 2w, C] view (channel slice allowed) -> [B, h, w, C] (mv_upsample2x_bwd)."""
+    lib = _lib_for(dup)
+    B, H2, W2, C = dup.shape
+    assert dup.stride(3) == 1 and dup.stride(1) == W2 * dup.stride(2) and dup.stride(0) == H2 * dup.stride(1)
+    if out is None:
+        out = torch.empty((B, H2 // 2, W2 // 2, C), dtype=torch.bfloat16, device=dup.device)
+    _lib.check(lib.mv_upsample2x_bwd(_ptr(dup), dup.stride(2), _ptr(out), B, H2 // 2, W2 // 2, C, _stream()),
+               "mv_upsample2x_bwd")
+    return out
+
+
+def zero_insert2x(dz, out=None):
+    lib = _lib_for(dz)
+    B, h, w, C = dz.shape
+    assert dz.is_contiguous()
+    if out is None:
+        out = torch.empty((B, 2 * h, 2 * w, C), dtype=torch.bfloat16, device=dz.device)
+    _lib.check(lib.mv_zero_insert2x(_ptr(dz), _ptr(out), B, h, w, C, _stream()), "mv_zero_insert2x")
+    return out
+
+
+def add_bf16(a, b, out=None):
+    """out = a + b for [M, C] bf16 matrices with arbitrary row pitch (mv_add_bf16)."""
+    lib = _lib_for(a)
+    M, C = a.shape
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.bfloat16, device=a.device)
+    _lib.check(lib.mv_add_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), M, C, _stream()), "mv_add_bf16")
+    return out
+
+
+def heads_ds(dpred, pred, dbias, out=None):
+    lib = _lib_for(dpred)
+    B, Hh, H, W = pred.shape
+    assert dpred.is_contiguous() and pred.is_contiguous() and dpred.dtype == torch.float32 and pred.dtype == torch.float32
+    if out is None:
+        out = torch.empty((B * H * W, 16), dtype=torch.bfloat16, device=pred.device)
+    _lib.check(lib.mv_heads_ds(_ptr(dpred), _ptr(pred), _ptr(out), _ptr(dbias), B, Hh, H * W, _stream()), "mv_heads_ds")
+    return out
+
+
+def heads_bwd_stencil(t, ds, gate, B, H, W, db2, dt=None, du=None):
+    lib = _lib_for(t)
+    M = B * H * W
+    assert t.shape == (M, 144) and t.is_contiguous() and ds.shape == (M, 16) and gate.shape == (M, 16) and gate.is_contiguous()
+    if dt is None:
+        dt = torch.empty((M, 144), dtype=torch.bfloat16, device=t.device)
+    if du is None:
+        du = torch.empty((M, 16), dtype=torch.bfloat16, device=t.device)
+    _lib.check(lib.mv_heads_bwd_stencil(_ptr(t), _ptr(ds), _ptr(gate), _ptr(dt), _ptr(du), _ptr(db2), B, H, W, _stream()),
+               "mv_heads_bwd_stencil")
+    return dt, du
