@@ -198,14 +198,16 @@ int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* 
  * src/generators/unet.py:411-415); activations are NHWC bf16 seen as [M, C] rows.  See csrc/bn.cu.
  *   mv_bn_finalize    (sum, sumsq) from the conv epilogue -> batch mean / rstd, folded (scale, shift), running-stat update
  *                     (momentum, unbiased variance). pre_bias: bias added before the BN (psi[0].bias) or NULL.
- *   mv_bn_relu_apply  y = relu(z*scale + shift)
+ *   mv_bn_relu_apply  y = relu(z*scale + shift); z is the raw conv output, bf16 or fp32 (z_f32) — the training path keeps
+ *                     it in fp32 so that bf16 rounding does not flip ReLU masks against the fp32 reference
  *   mv_bn_relu_bwd    dz = BN'(dy * [y > 0]); sums (fp32 [2, C], overwritten) = (dbeta, dgamma)
  * ---------------------------------------------------------------------------------------------------------- */
 int mv_bn_finalize(const float* colstats, double count, const float* gamma, const float* beta, const float* pre_bias,
                    float* running_mean, float* running_var, float momentum, float eps, int c, float* scale, float* shift,
                    float* mean, float* rstd, void* stream);
-int mv_bn_relu_apply(const void* z, const float* scale, const float* shift, void* y, int64_t m, int c, void* stream);
-int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, const float* mean, const float* rstd,
+int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int64_t m, int c,
+                     void* stream);
+int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, int z_f32, const float* mean, const float* rstd,
                    const float* gamma, float* sums, void* dz, int64_t m, int c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -131,28 +131,41 @@ def encoder_backward(eng, tape, dmap, on_start=None):
     return grads
 
 
-class _EncoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, eng, x, *lora_params):
-        tape = eng._train_tape(x.shape[0])
-        fmap = encoder_forward_train(eng, x, tape)
-        ctx.eng, ctx.tape = eng, tape
-        return fmap.permute(0, 3, 1, 2).float()  # NCHW fp32 for the decoder
+class _MipheiFn(torch.autograd.Function):
+    """Whole generator in training mode: encoder + decoder forward on the kernels, one backward for every trainable
+    parameter (LoRA A/B of each block + the decoder)."""
 
     @staticmethod
-    def backward(ctx, dfeat):
-        eng, tape = ctx.eng, ctx.tape
-        dmap = dfeat.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-        grads = encoder_backward(eng, tape, dmap, on_start=eng.on_encoder_backward_start)
-        flat = []
-        for g in grads:
-            flat.extend(g)
-        return (None, None) + tuple(flat)
+    def forward(ctx, eng, x, *params):
+        tape = eng._train_tape(x.shape[0])
+        fmap = encoder_forward_train(eng, x, tape)
+        ws = eng._workspace(x.shape[0])
+        pred = eng.decoder_train.forward(fmap, ws.img8)
+        ctx.eng, ctx.tape, ctx.params = eng, tape, params
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        eng, tape, params = ctx.eng, ctx.tape, ctx.params
+        grads, dfmap = eng.decoder_train.backward(dpred.float())
+        sink = eng.direct_grad_sink  # trainer mode: write straight into the flat gradient buffer
+        if sink:
+            for p, g in grads.items():
+                p.grad.copy_(g)
+            grads = {}
+        lgrads = encoder_backward(eng, tape, dfmap, on_start=eng.on_encoder_backward_start)
+        for pb, (gAq, gBq, gAv, gBv) in zip(eng.blocks, lgrads):
+            lq, lv = pb["lora"]
+            for p, g in ((lq.A, gAq), (lq.B, gBq), (lv.A, gAv), (lv.B, gBv)):
+                if sink:
+                    p.grad.copy_(g)
+                else:
+                    grads[p] = g
+        return (None, None) + tuple(grads.get(p) for p in params)
 
 
 def decoder_forward_torch(dec, feat, images):
-    """Detail_Capture.forward (mipheivit.py:207-220) on PyTorch CUDA ops, train-mode BatchNorm — interim path.
-    fp32 tensors (cuDNN may use TF32 products): bf16 autocast here costs the 0.999 gradient-cosine bar."""
+    """Detail_Capture.forward on PyTorch CUDA ops — kept ONLY as a debugging cross-check (tools/), never on the product path."""
     with torch.autocast("cuda", enabled=False):
         details = [images]
         x = images
@@ -173,6 +186,9 @@ def decoder_forward_torch(dec, feat, images):
 
 
 def miphei_train_forward(eng, x):
+    if not eng.model.training:
+        raise NotImplementedError("gradients through the eval-mode (running-statistics BatchNorm) generator are not "
+                                  "implemented; call model.train() for training or torch.no_grad() for inference")
     if not getattr(eng, "_bwd_packed", False):
         _pack_backward_weights(eng)
         eng._lora_bwd_versions = None
@@ -180,12 +196,19 @@ def miphei_train_forward(eng, x):
     if eng._lora_bwd_versions != ver:
         _refresh_lora_backward(eng)
         eng._lora_bwd_versions = ver
+    if eng.decoder_train is None:
+        from .decoder_train import DecoderTrain
+        eng.decoder_train = DecoderTrain(eng)
+        eng._dec_train_versions = None
+    if eng._dec_train_versions != eng._lora_versions or eng._dec_train_versions is None:
+        eng.decoder_train.pack()
+        eng._dec_train_versions = eng._lora_versions
     xf = x.float().contiguous()
-    lora_params = []
-    for pb in eng.blocks:
-        lq, lv = pb["lora"]
-        lora_params += [lq.A, lq.B, lv.A, lv.B]
-    feat = _EncoderFn.apply(eng, xf, *lora_params)
-    pred = decoder_forward_torch(eng.model.decoder, feat, xf)
+    if torch.is_grad_enabled():
+        pred = _MipheiFn.apply(eng, xf, *eng._trainables)
+    else:  # train-mode forward without autograd (BatchNorm batch statistics, running stats updated)
+        tape = eng._train_tape(xf.shape[0])
+        fmap = encoder_forward_train(eng, xf, tape)
+        pred = eng.decoder_train.forward(fmap, eng._workspace(xf.shape[0]).img8)
     out_dtype = eng._out_dtype(x)
     return pred if pred.dtype == out_dtype else pred.to(out_dtype)

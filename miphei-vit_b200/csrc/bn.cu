@@ -36,22 +36,36 @@ __global__ void bn_finalize_kernel(const float* __restrict__ colstats, float cou
   }
 }
 
+// 8 consecutive channels of row-major z (bf16 or fp32) at vector index i
+template <bool ZF32>
+__device__ __forceinline__ void load_z8(const void* z, long long i, float* f) {
+  if (ZF32) {
+    const float4 a = reinterpret_cast<const float4*>(z)[2 * i], b = reinterpret_cast<const float4*>(z)[2 * i + 1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 u = reinterpret_cast<const uint4*>(z)[i];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = d.x; f[5] = d.y; f[6] = e.x; f[7] = e.y;
+  }
+}
+
 // one thread = 8 consecutive channels of one row
-__global__ void bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+template <bool ZF32>
+__global__ void bn_relu_apply_kernel(const void* __restrict__ z, const float* __restrict__ scale,
                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long M, int C) {
   const int cg = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * cg) return;
   const int c = (int)(i % cg) * 8;
-  const uint4 u = reinterpret_cast<const uint4*>(z)[i];
+  float f[8];
+  load_z8<ZF32>(z, i, f);
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
   const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
   uint4 o;
-  o.x = pack_bf16x2(fmaxf(a.x * s0.x + h0.x, 0.f), fmaxf(a.y * s0.y + h0.y, 0.f));
-  o.y = pack_bf16x2(fmaxf(b.x * s0.z + h0.z, 0.f), fmaxf(b.y * s0.w + h0.w, 0.f));
-  o.z = pack_bf16x2(fmaxf(d.x * s1.x + h1.x, 0.f), fmaxf(d.y * s1.y + h1.y, 0.f));
-  o.w = pack_bf16x2(fmaxf(e.x * s1.z + h1.z, 0.f), fmaxf(e.y * s1.w + h1.w, 0.f));
+  o.x = pack_bf16x2(fmaxf(f[0] * s0.x + h0.x, 0.f), fmaxf(f[1] * s0.y + h0.y, 0.f));
+  o.y = pack_bf16x2(fmaxf(f[2] * s0.z + h0.z, 0.f), fmaxf(f[3] * s0.w + h0.w, 0.f));
+  o.z = pack_bf16x2(fmaxf(f[4] * s1.x + h1.x, 0.f), fmaxf(f[5] * s1.y + h1.y, 0.f));
+  o.w = pack_bf16x2(fmaxf(f[6] * s1.z + h1.z, 0.f), fmaxf(f[7] * s1.w + h1.w, 0.f));
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
@@ -59,9 +73,10 @@ constexpr int BNB_THREADS = 256;
 constexpr int BNB_ROWS = 512;  // rows per block
 
 // sums[0..C) += sum_rows dzh, sums[C..2C) += sum_rows dzh * xhat.  blockDim.x = 256 = (C/8) column groups x row lanes
+template <bool ZF32>
 __global__ void __launch_bounds__(BNB_THREADS) bn_relu_bwd_stats_kernel(
     const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
-    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+    const void* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ sums, long long M, int C) {
   extern __shared__ float red[];  // [2][256][8]
   const int cg = C / 8;
@@ -78,15 +93,16 @@ __global__ void __launch_bounds__(BNB_THREADS) bn_relu_bwd_stats_kernel(
     for (long long r = r0 + rl; r < r1; r += rlanes) {
       const uint4 ud = *reinterpret_cast<const uint4*>(dy + r * lddy + c);
       const uint4 uy = *reinterpret_cast<const uint4*>(y + r * C + c);
-      const uint4 uz = *reinterpret_cast<const uint4*>(z + r * C + c);
-      const uint32_t* pd = &ud.x; const uint32_t* py = &uy.x; const uint32_t* pz = &uz.x;
+      float fz[8];
+      load_z8<ZF32>(z, (r * C + c) / 8, fz);
+      const uint32_t* pd = &ud.x; const uint32_t* py = &uy.x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]), fz = unpack_bf16x2(pz[j]);
+        const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]);
         const float g0 = fy.x > 0.f ? fd.x : 0.f, g1 = fy.y > 0.f ? fd.y : 0.f;
         s1[2 * j] += g0; s1[2 * j + 1] += g1;
-        s2[2 * j] += g0 * (fz.x - mu[2 * j]) * rs[2 * j];
-        s2[2 * j + 1] += g1 * (fz.y - mu[2 * j + 1]) * rs[2 * j + 1];
+        s2[2 * j] += g0 * (fz[2 * j] - mu[2 * j]) * rs[2 * j];
+        s2[2 * j + 1] += g1 * (fz[2 * j + 1] - mu[2 * j + 1]) * rs[2 * j + 1];
       }
     }
   }
@@ -109,8 +125,9 @@ __global__ void __launch_bounds__(BNB_THREADS) bn_relu_bwd_stats_kernel(
   }
 }
 
+template <bool ZF32>
 __global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                                         const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
+                                         const __nv_bfloat16* __restrict__ y, const void* __restrict__ z,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ sums, float inv_n,
                                          __nv_bfloat16* __restrict__ dz, long long M, int C) {
@@ -121,18 +138,19 @@ __global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, l
   const long long r = i / cg;
   const uint4 ud = *reinterpret_cast<const uint4*>(dy + r * lddy + c);
   const uint4 uy = reinterpret_cast<const uint4*>(y)[i];
-  const uint4 uz = reinterpret_cast<const uint4*>(z)[i];
-  const uint32_t* pd = &ud.x; const uint32_t* py = &uy.x; const uint32_t* pz = &uz.x;
+  float fz[8];
+  load_z8<ZF32>(z, i, fz);
+  const uint32_t* pd = &ud.x; const uint32_t* py = &uy.x;
   uint32_t o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]), fz = unpack_bf16x2(pz[j]);
+    const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]);
     float r2[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int cc = c + 2 * j + e;
       const float g = (e ? fy.y : fy.x) > 0.f ? (e ? fd.y : fd.x) : 0.f;
-      const float xh = ((e ? fz.y : fz.x) - mean[cc]) * rstd[cc];
+      const float xh = (fz[2 * j + e] - mean[cc]) * rstd[cc];
       r2[e] = gamma[cc] * rstd[cc] * (g - sums[cc] * inv_n - xh * sums[C + cc] * inv_n);
     }
     o[j] = pack_bf16x2(r2[0], r2[1]);
@@ -155,20 +173,22 @@ extern "C" int mv_bn_finalize(const float* colstats, double count, const float* 
   return MV_OK;
 }
 
-extern "C" int mv_bn_relu_apply(const void* z, const float* scale, const float* shift, void* y, int64_t m, int c,
+extern "C" int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int64_t m, int c,
                                 void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(z && scale && shift && y && m > 0 && c % 8 == 0, "mv_bn_relu_apply: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = m * (c / 8);
-  bn_relu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
+  if (z_f32) bn_relu_apply_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
+  else bn_relu_apply_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
   MV_CHECK_LAUNCH("bn_relu_apply");
   return MV_OK;
 }
 
 // sums: fp32 [2, C], zeroed by this call
-extern "C" int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, const float* mean,
+extern "C" int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, int z_f32, const float* mean,
                               const float* rstd, const float* gamma, float* sums, void* dz, int64_t m, int c,
                               void* stream_) {
   using namespace mv;
@@ -181,15 +201,19 @@ extern "C" int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const
     return (int)e;
   }
   const int smem = 2 * BNB_THREADS * 8 * 4;
-  bn_relu_bwd_stats_kernel<<<(unsigned)((m + BNB_ROWS - 1) / BNB_ROWS), BNB_THREADS, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y),
-      reinterpret_cast<const __nv_bfloat16*>(z), mean, rstd, sums, m, c);
+  const unsigned sgrid = (unsigned)((m + BNB_ROWS - 1) / BNB_ROWS);
+  if (z_f32) bn_relu_bwd_stats_kernel<true><<<sgrid, BNB_THREADS, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, sums, m, c);
+  else bn_relu_bwd_stats_kernel<false><<<sgrid, BNB_THREADS, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, sums, m, c);
   MV_CHECK_LAUNCH("bn_relu_bwd_stats");
   const long long total = m * (c / 8);
-  bn_relu_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y),
-      reinterpret_cast<const __nv_bfloat16*>(z), mean, rstd, gamma, sums, (float)(1.0 / (double)m),
-      reinterpret_cast<__nv_bfloat16*>(dz), m, c);
+  if (z_f32) bn_relu_bwd_apply_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, gamma, sums,
+      (float)(1.0 / (double)m), reinterpret_cast<__nv_bfloat16*>(dz), m, c);
+  else bn_relu_bwd_apply_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, gamma, sums,
+      (float)(1.0 / (double)m), reinterpret_cast<__nv_bfloat16*>(dz), m, c);
   MV_CHECK_LAUNCH("bn_relu_bwd_apply");
   return MV_OK;
 }

@@ -340,6 +340,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (p.out_f32) {
             const int col = (lane & 7) * 4;
             const int nn = n0 + col;
+            float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f), cq4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (nn < p.n) {
               float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
@@ -371,6 +372,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
                   if (p.act == MV_ACT_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
                   a.x += q_[it].x; a.y += q_[it].y; a.z += q_[it].z; a.w += q_[it].w;
+                  cs4.x += a.x; cs4.y += a.y; cs4.z += a.z; cs4.w += a.w;
+                  cq4.x += a.x * a.x; cq4.y += a.y * a.y; cq4.z += a.z * a.z; cq4.w += a.w * a.w;
                   const long long orow = orow_[it];
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nn) = a;
                   if (p.aux) {
@@ -380,6 +383,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + orow * p.ldaux + nn) = u;
                   }
                 }
+              }
+            }
+            if (p.colstats) {  // rows live in lane >> 3: fold the 4 row groups, one atomic per column per warp
+#pragma unroll
+              for (int o = 8; o < 32; o <<= 1) {
+                cs4.x += __shfl_xor_sync(0xffffffffu, cs4.x, o); cs4.y += __shfl_xor_sync(0xffffffffu, cs4.y, o);
+                cs4.z += __shfl_xor_sync(0xffffffffu, cs4.z, o); cs4.w += __shfl_xor_sync(0xffffffffu, cs4.w, o);
+                cq4.x += __shfl_xor_sync(0xffffffffu, cq4.x, o); cq4.y += __shfl_xor_sync(0xffffffffu, cq4.y, o);
+                cq4.z += __shfl_xor_sync(0xffffffffu, cq4.z, o); cq4.w += __shfl_xor_sync(0xffffffffu, cq4.w, o);
+              }
+              if (lane < 8 && nn < p.n) {
+                atomicAdd(p.colstats + nn + 0, cs4.x); atomicAdd(p.colstats + nn + 1, cs4.y);
+                atomicAdd(p.colstats + nn + 2, cs4.z); atomicAdd(p.colstats + nn + 3, cs4.w);
+                atomicAdd(p.colstats + p.n + nn + 0, cq4.x); atomicAdd(p.colstats + p.n + nn + 1, cq4.y);
+                atomicAdd(p.colstats + p.n + nn + 2, cq4.z); atomicAdd(p.colstats + p.n + nn + 3, cq4.w);
               }
             }
           } else {
@@ -429,7 +447,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (p.colstats) {  // BatchNorm batch statistics of exactly what is stored (bf16-rounded)
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
-                    const float fr = __bfloat162float(__float2bfloat16(f[j]));
+                    const float fr = p.out ? __bfloat162float(__float2bfloat16(f[j])) : f[j];
                     csum[j] += fr;
                     csq[j] += fr * fr;
                   }
@@ -731,7 +749,7 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   const mv_gemm_args& a = *args;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MV_CHECK_ARG(a.a && a.b && (a.out || a.colstats), "mv_gemm_bf16: null operand");
-  MV_CHECK_ARG(!a.colstats || (a.mode == MV_GEMM_LINEAR && !a.out_f32 && a.n >= 32), "mv_gemm_bf16: colstats needs LINEAR mode, bf16 output, N >= 32");
+  MV_CHECK_ARG(!a.colstats || (a.mode == MV_GEMM_LINEAR && a.n >= 32), "mv_gemm_bf16: colstats needs LINEAR mode, N >= 32");
   MV_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0, "mv_gemm_bf16: empty problem m=%d n=%d k=%d", a.m, a.n, a.k);
   MV_CHECK_ARG(a.n % 8 == 0 || a.mode == MV_GEMM_HEAD_CONV, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
   MV_CHECK_ARG(a.k % 8 == 0 || a.mode == MV_GEMM_NN_ATOMIC, "mv_gemm_bf16: K=%d must be a multiple of 8", a.k);

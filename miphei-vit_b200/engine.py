@@ -67,6 +67,11 @@ class MipheiEngine:
         self._bwd_packed = False
         self._lora_bwd_versions = None
         self.on_encoder_backward_start = None  # trainer hook: decoder gradients are complete at this point
+        self.weights_generation = 0
+        self._lora_versions = None
+        self.direct_grad_sink = False          # trainer mode: backward writes into p.grad (flat buffer views) directly
+        self.decoder_train = None
+        self._dec_train_versions = None
 
     # ------------------------------------------------------------------ geometry
     def _geometry(self):
@@ -91,6 +96,7 @@ class MipheiEngine:
         self._tapes = {}
         self._bwd_packed = False
         self._lora_bwd_versions = None
+        self._dec_train_versions = None
 
     def _train_tape(self, B):
         tape = self._tapes.get(B)
@@ -103,7 +109,11 @@ class MipheiEngine:
     # ------------------------------------------------------------------ packing
     def _trainable_version(self):
         return tuple(p._version for p in self._trainables) + tuple(
-            b._version for b in self._bn_buffers) + (self.model.training,)
+            b._version for b in self._bn_buffers) + (self.weights_generation,)
+
+    def bump_weights(self):
+        """Trainable weights were updated outside autograd's version tracking (fused optimiser kernel)."""
+        self.weights_generation += 1
 
     def _pack_frozen(self):
         self._geometry()
@@ -145,10 +155,9 @@ class MipheiEngine:
         self._packed = True
         self._train_versions = None
 
-    def _pack_trainable(self):
-        """LoRA columns of the extended QKV weight + decoder weights (BatchNorm folded with running statistics)."""
+    def _pack_lora(self):
+        """LoRA columns of the K-extended QKV weight (forward)."""
         D = self.D
-        dec = self.model.decoder
         with torch.no_grad():
             for pb in self.blocks:
                 lq, lv = pb["lora"]
@@ -156,6 +165,11 @@ class MipheiEngine:
                 pb["acat"][8:] = lv.A.detach().t()
                 pb["wqkv_ext"][:D, D:D + 8] = (lq.alpha * lq.B.detach()).t()
                 pb["wqkv_ext"][2 * D:, D + 8:D + 16] = (lv.alpha * lv.B.detach()).t()
+
+    def _pack_trainable(self):
+        """Decoder weights for the eval path (BatchNorm folded with running statistics)."""
+        dec = self.model.decoder
+        with torch.no_grad():
             self.cs = []
             for i, m in enumerate(dec.convstream.convs):
                 cin = m.conv.weight.shape[1]
@@ -178,14 +192,20 @@ class MipheiEngine:
             self.hd = packing.pack_heads(hps)
         self._train_versions = self._trainable_version()
 
-    def _ensure_packed(self):
+    def _ensure_packed(self, train=False):
         if not self._packed:
             self._pack_frozen()
-        if self._train_versions != self._trainable_version():
+            self._lora_versions = None
+        ver = self._trainable_version()
+        if self._lora_versions != ver:
+            self._pack_lora()
+            self._lora_versions = ver
+        if not train and self._train_versions != ver:
             self._pack_trainable()
             for ws in self._ws.values():
-                ws.graph = None  # captured graphs bake nothing weight-dependent except pointers, which are stable;
-                # kept simple: re-capture after a weight update
+                ws.graph = None  # re-capture after a weight update (packed tensors are re-created)
+                if hasattr(ws, "graph_u8"):
+                    ws.graph_u8 = None
 
     def _workspace(self, B):
         ws = self._ws.get(B)
@@ -251,7 +271,7 @@ class MipheiEngine:
             raise AssertionError("Input size (%s) doesn't match model (%d)" % (tuple(x.shape), self.S))
 
     def forward(self, x):
-        self._ensure_packed()
+        self._ensure_packed(train=self.model.training)
         self._check_input(x)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._trainables)
         if self.model.training or needs_grad:

@@ -316,8 +316,9 @@ def bn_relu_apply(z, scale, shift, out=None):
     M, C = z.shape
     assert z.is_contiguous()
     if out is None:
-        out = torch.empty_like(z)
-    _lib.check(lib.mv_bn_relu_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(out), M, C, _stream()), "mv_bn_relu_apply")
+        out = torch.empty((M, C), dtype=torch.bfloat16, device=z.device)
+    _lib.check(lib.mv_bn_relu_apply(_ptr(z), 1 if z.dtype == torch.float32 else 0, _ptr(scale), _ptr(shift), _ptr(out), M, C,
+                                    _stream()), "mv_bn_relu_apply")
     return out
 
 
@@ -329,9 +330,9 @@ def bn_relu_bwd(dy, y, z, mean, rstd, gamma, sums=None, dz=None):
     if sums is None:
         sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
     if dz is None:
-        dz = torch.empty_like(z)
-    _lib.check(lib.mv_bn_relu_bwd(_ptr(dy), dy.stride(0), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums),
-                                  _ptr(dz), M, C, _stream()), "mv_bn_relu_bwd")
+        dz = torch.empty((M, C), dtype=torch.bfloat16, device=z.device)
+    _lib.check(lib.mv_bn_relu_bwd(_ptr(dy), dy.stride(0), _ptr(y), _ptr(z), 1 if z.dtype == torch.float32 else 0, _ptr(mean),
+                                  _ptr(rstd), _ptr(gamma), _ptr(sums), _ptr(dz), M, C, _stream()), "mv_bn_relu_bwd")
     return dz, sums
 
 

@@ -67,6 +67,7 @@ class Trainer:
         self._dec_work = None
         self.eng.on_encoder_backward_start = self._decoder_grads_ready
         self.eng.invalidate()
+        self.eng.direct_grad_sink = True
 
     # called by the encoder's autograd node when it starts its backward: every decoder gradient is final
     def _decoder_grads_ready(self):
@@ -82,7 +83,6 @@ class Trainer:
     def step(self, x, y):
         """One optimisation step on device tensors x [B,3,S,S], y [B,C,S,S]; returns the loss tensor (no host sync)."""
         self.model.train()
-        self.gflat.zero_()
         pred = self.model(x)
         p32 = pred.detach().float().contiguous()
         loss, dpred = ops.loss_fwd_bwd(p32, y, self.marker_weights, mode=self.loss_mode, lambda_factor=self.lambda_factor,
@@ -99,10 +99,8 @@ class Trainer:
         lr = self.base_lr * lr_lambda(self.step_count - 1, self.total_steps, self.warmup_steps)
         ops.adam_clip_step(self.flat, self.gflat, self.m, self.v, self.norm, self.step_count, lr, self.betas[0],
                            self.betas[1], self.eps)
-        # parameters changed in place through the flat buffer: bump versions so the engine re-packs the trainables
-        for _, p in self.order[:1]:
-            p.data.add_(0)
-        self.eng._train_versions = None
+        # parameters changed in place through the flat buffer, behind autograd's version counters
+        self.eng.bump_weights()
         self.eng._lora_bwd_versions = None
         return loss
 

@@ -30,8 +30,9 @@ def _rel(got, ref):
     return (got.float() - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
 
 
+@pytest.mark.parametrize("zdt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 32, 64, 48), (2, 16, 192, 256), (1, 64, 8, 96)])
-def test_conv_bn_relu_train_forward_backward(B, H, Cin, Cout):
+def test_conv_bn_relu_train_forward_backward(B, H, Cin, Cout, zdt):
     ops, packing = _mods()
     x = _rand((B, Cin, H, H), 1.0, 1).bfloat16().float()
     w = _rand((Cout, Cin, 3, 3), 0.05, 2).bfloat16().float()
@@ -50,7 +51,7 @@ def test_conv_bn_relu_train_forward_backward(B, H, Cin, Cout):
     xn = _nhwc(x)
     M = B * H * H
     stats = torch.zeros((2, Cout), device="cuda")
-    z = ops.gemm(xn, packing.pack_conv3x3(w, [Cin]), conv=dict(stride=1), colstats=stats)
+    z = ops.gemm(xn, packing.pack_conv3x3(w, [Cin]), conv=dict(stride=1), colstats=stats, out_dtype=zdt)
     fin = ops.bn_finalize(stats, M, gamma, beta, rm, rv)
     y = ops.bn_relu_apply(z, fin[0], fin[1])
     assert _rel(y.view(B, H, H, Cout).permute(0, 3, 1, 2), yr.detach()) < 2e-2

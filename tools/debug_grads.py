@@ -36,6 +36,9 @@ loss, dpred = ops.loss_fwd_bwd(pred.detach().float().contiguous(), y.cuda(), tr.
 pred.backward(dpred.to(pred.dtype))
 print("loss", loss.item(), rl.item(), "pred pearson", om.pearson(pred.detach().float().cpu(), rp.detach()))
 print("dfeat cosine", om.cosine(cap["dmap"].permute(0, 3, 1, 2), dfeat_ref))
+allg = torch.cat([p.grad.float().cpu().flatten() for n, p in tr.order]); allr = torch.cat([gref[n].flatten() for n, p in tr.order])
+print("GLOBAL cosine", om.cosine(allg, allr))
 for n, p in tr.order:
-    if ".lora_" in n or "fusion_blks.0" in n or "convs.0" in n or "head_0" in n:
+    if "segmentation_head" in n and "head_0" not in n and "head_1." not in n: continue
+    if True:
         print("%-60s cos %.5f  |g| %.3e ref %.3e" % (n, om.cosine(p.grad.float().cpu(), gref[n]), float(p.grad.norm()), float(gref[n].norm())))
