@@ -54,7 +54,8 @@ struct GemmCfg {
   static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
   static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
   static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
+  static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -148,6 +149,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* staging_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::kStageBytes + 256);
+  float* cstat = staging_all + 4 * 32 * 36;  // [2][BLOCK_N]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -310,12 +312,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
+    const int ep_tid = threadIdx.x - 64;  // 0..127
     int as = 0;
     uint32_t aphase = 0;
+    int stat_nblk = -1;
+    auto flush_stats = [&](int nb) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) {
+        const float v = cstat[i];
+        const int col = nb * BLOCK_N + (i % BLOCK_N);
+        if (v != 0.f && col < p.n) atomicAdd(p.colstats + (i / BLOCK_N) * p.n + col, v);
+        cstat[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    if (MODE == MV_GEMM_LINEAR && p.colstats) {
+      for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) cstat[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile % num_mn;
       const int m_blk = mn % p.num_m_blocks;
       const int n_blk = mn / p.num_m_blocks;
+      if (MODE == MV_GEMM_LINEAR && p.colstats && n_blk != stat_nblk) {
+        if (stat_nblk >= 0) flush_stats(stat_nblk);
+        stat_nblk = n_blk;
+      }
       const int m = m_blk * GEMM_BLOCK_M + row_in_tile;
       const bool row_ok = m < p.m;
       mbar_wait(tfull_bar(as), aphase);
@@ -394,10 +416,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 cq4.z += __shfl_xor_sync(0xffffffffu, cq4.z, o); cq4.w += __shfl_xor_sync(0xffffffffu, cq4.w, o);
               }
               if (lane < 8 && nn < p.n) {
-                atomicAdd(p.colstats + nn + 0, cs4.x); atomicAdd(p.colstats + nn + 1, cs4.y);
-                atomicAdd(p.colstats + nn + 2, cs4.z); atomicAdd(p.colstats + nn + 3, cs4.w);
-                atomicAdd(p.colstats + p.n + nn + 0, cq4.x); atomicAdd(p.colstats + p.n + nn + 1, cq4.y);
-                atomicAdd(p.colstats + p.n + nn + 2, cq4.z); atomicAdd(p.colstats + p.n + nn + 3, cq4.w);
+                float* cs = cstat + c * 32 + col;
+                atomicAdd(cs + 0, cs4.x); atomicAdd(cs + 1, cs4.y); atomicAdd(cs + 2, cs4.z); atomicAdd(cs + 3, cs4.w);
+                atomicAdd(cs + BLOCK_N + 0, cq4.x); atomicAdd(cs + BLOCK_N + 1, cq4.y);
+                atomicAdd(cs + BLOCK_N + 2, cq4.z); atomicAdd(cs + BLOCK_N + 3, cq4.w);
               }
             }
           } else {
@@ -465,10 +487,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
               }
               if (lane < 4 && col_ok) {
+                float* cs = cstat + c * 32 + col;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  atomicAdd(p.colstats + nn + j, csum[j]);
-                  atomicAdd(p.colstats + p.n + nn + j, csq[j]);
+                  atomicAdd(cs + j, csum[j]);
+                  atomicAdd(cs + BLOCK_N + j, csq[j]);
                 }
               }
             }
@@ -616,41 +639,65 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       } else {  // MV_GEMM_SWIGLU_BWD: acc = dU tile (128 hidden units); N == H
         const int H = p.n;
-        constexpr int CH = 32;
+        float* stg = staging_all + quad * (32 * 36);
+        const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / CH; ++c) {
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
-          tmem_ld32(taddr + c * CH, v);
+          tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (row_ok) {
-            const int j0 = n_blk * BLOCK_N + c * CH;
-            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)m * p.ldin2;
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              const int jj = j0 + j8 * 8;
-              if (jj >= H) break;
-              float fg[8], fv[8], dg[8], dv[8];
-              load_bf16x8(h + jj, fg);
-              load_bf16x8(h + H + jj, fv);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int col = (lane & 3) * 8;
+          const int jj = n_blk * BLOCK_N + c * 32 + col;
+          // the saved pre-activations are fetched for all 4 row groups before any store (loads stay in flight together)
+          uint4 hg[4], hv[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float du = __uint_as_float(v[j8 * 8 + j]);
-                const float sg = 1.f / (1.f + __expf(-fg[j]));
-                const float sl = fg[j] * sg;
-                dg[j] = du * fv[j] * (sg * (1.f + fg[j] * (1.f - sg)));
-                dv[j] = du * sl;
+          for (int it = 0; it < 4; ++it) {
+            const int mm = m_warp + it * 8 + (lane >> 2);
+            hg[it] = make_uint4(0, 0, 0, 0);
+            hv[it] = hg[it];
+            if (mm < p.m && jj < H) {
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)mm * p.ldin2;
+              hg[it] = *reinterpret_cast<const uint4*>(h + jj);
+              hv[it] = *reinterpret_cast<const uint4*>(h + H + jj);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int mm = m_warp + r;
+            if (mm < p.m && jj < H) {
+              const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+              const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 36 + col + 4);
+              const float du[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const uint32_t* pg = &hg[it].x;
+              const uint32_t* pv = &hv[it].x;
+              float dg[8], dv[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 fg = unpack_bf16x2(pg[j]), fv = unpack_bf16x2(pv[j]);
+                const float s0 = 1.f / (1.f + __expf(-fg.x)), s1 = 1.f / (1.f + __expf(-fg.y));
+                dg[2 * j] = du[2 * j] * fv.x * (s0 * (1.f + fg.x * (1.f - s0)));
+                dg[2 * j + 1] = du[2 * j + 1] * fv.y * (s1 * (1.f + fg.y * (1.f - s1)));
+                dv[2 * j] = du[2 * j] * fg.x * s0;
+                dv[2 * j + 1] = du[2 * j + 1] * fg.y * s1;
               }
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)mm * p.ldo;
               store_bf16x8(o + jj, dg);
               store_bf16x8(o + H + jj, dv);
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (MODE == MV_GEMM_LINEAR && p.colstats && stat_nblk >= 0) flush_stats(stat_nblk);
   }
 
   tc_fence_before();

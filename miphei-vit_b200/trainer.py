@@ -173,5 +173,5 @@ def bench_train(model, args, rank, world, dev):
     return {"metric": "tiles_per_sec_train_256px_16ch", "value": world * B / ms * 1e3, "unit": "tiles/s",
             "ms_per_step": ms, "steps": steps, "batch_per_gpu": B, "loss": float(loss.item()),
             "tflops": world * B * 1633.87 / ms, "scaling": "weak",
-            "note": "fwd+bwd+WeightedMSE+clip+Adam; encoder fwd/bwd, loss and optimiser on hand-written kernels, decoder "
-                    "train-mode fwd/bwd on PyTorch CUDA ops (interim); NCCL AVG all-reduce of 26.8 MB in 2 buckets"}
+            "note": "fwd+bwd+WeightedMSE+clip+Adam, every kernel hand-written (encoder, decoder with train-mode BatchNorm, "
+                    "loss, optimiser); NCCL AVG all-reduce of 26.8 MB in 2 buckets overlapped with the encoder backward"}
