@@ -10,6 +10,7 @@
 // QkvWithLoRA (src/generators/lora.py:29-33) through a K-extended weight, and the decoder convs through im2col.
 #include "mv_host.h"
 #include "mv_ptx.cuh"
+#include <stdlib.h>
 
 namespace mv {
 
@@ -42,12 +43,15 @@ struct GemmDev {
   int conv_cb0, conv_cb1;  // 64-channel blocks per tap taken from source 0 / source 1 (channel concat)
 };
 
-template <int BLOCK_N, int MODE = 0>
+// PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
+// the B rows (the tensor core reads the other half from the peer's shared memory), halving B traffic per SM.
+template <int BLOCK_N, int MODE = 0, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int kBoxRowsB = BLOCK_N < 128 ? BLOCK_N : 128;
-  static constexpr int kBoxesB = BLOCK_N / kBoxRowsB;
+  static constexpr int kRowsB = PAIR ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by this CTA
+  static constexpr int kBoxRowsB = kRowsB < 128 ? kRowsB : 128;
+  static constexpr int kBoxesB = kRowsB / kBoxRowsB;
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
@@ -128,12 +132,16 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR>;
   constexpr int STAGES = Cfg::kStages;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile_start = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
@@ -157,22 +165,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_b);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);  // pair: the leader expects the bytes of both CTAs, the peer's TMA only completes tx
       mbar_init(empty_bar(s), 1);
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), PAIR ? 8 : 4);  // one arrival per epilogue warp (pair: the peer's warps arrive remotely)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, Cfg::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -185,9 +193,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int split = tile / num_mn, mn = tile - split * num_mn;
-        const int m_blk = mn % p.num_m_blocks;
+        const int m_blk = PAIR ? (mn % p.num_m_blocks) * 2 + (int)cta_rank : mn % p.num_m_blocks;  // 128-row block
         const int n_blk = mn / p.num_m_blocks;
         const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
         const int m0 = m_blk * GEMM_BLOCK_M;
@@ -195,8 +203,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (MODE == MV_GEMM_SWIGLU) {  // 128 gate rows + the matching 128 value rows
           brow[0] = n_blk * 128;
           brow[1] = p.n / 2 + n_blk * 128;
+          if (PAIR) brow[0] = brow[cta_rank];  // leader stages the gate rows, the peer the value rows
         } else {
-          brow[0] = n_blk * BLOCK_N;
+          brow[0] = n_blk * BLOCK_N + (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
           brow[1] = n_blk * BLOCK_N + 128;
         }
         int cv_b = 0, cv_y = 0, cv_x = 0;
@@ -213,6 +222,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const bool nn_conv = MODE == MV_GEMM_NN_ATOMIC && p.conv;
+          if (PAIR) {
+            // both CTAs' TMA bytes land on the LEADER's full barrier; it expects the sum, the peer only arrives
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
+            tma_load_2d_pair(sb, &tmap_b, full_bar(stage), kb * GEMM_BLOCK_K, brow[0]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!nn_conv) mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           if (nn_conv) {
           } else if (p.conv) {
@@ -267,13 +284,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int split = tile / num_mn;
         const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
         mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -297,14 +314,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int ns = 0; ns < BLOCK_N / 64; ++ns)
                 umma_bf16(d_tmem + ns * 64, da + 2 * k, umma_desc_sw128(sb + ns * 8192 + k * 2048, 1024, 1024), idesc_mn,
                           (kb != kb0) || (k != 0));
+            } else if constexpr (PAIR) {
+              umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
             } else {
               umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
             }
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (pair: signalled in both CTAs)
+          if (PAIR) umma_commit_pair(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(as));  // accumulator complete
+        if (PAIR) umma_commit_pair(tfull_bar(as), 3); else umma_commit(tfull_bar(as));  // accumulator complete
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -330,9 +350,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) cstat[i] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
       const int mn = tile % num_mn;
-      const int m_blk = mn % p.num_m_blocks;
+      const int m_blk = PAIR ? (mn % p.num_m_blocks) * 2 + (int)cta_rank : mn % p.num_m_blocks;  // 128-row block
       const int n_blk = mn / p.num_m_blocks;
       if (MODE == MV_GEMM_LINEAR && p.colstats && n_blk != stat_nblk) {
         if (stat_nblk >= 0) flush_stats(stat_nblk);
@@ -694,26 +714,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (MODE == MV_GEMM_LINEAR && p.colstats && stat_nblk >= 0) flush_stats(stat_nblk);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------ host launch
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool PAIR = false>
 static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE, PAIR>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -754,7 +777,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
 
   GemmDev p;
   p.m = a.m; p.n = a.n; p.k = a.k;
-  p.num_m_blocks = (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.num_m_blocks = PAIR ? (a.m + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M) : (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   p.num_n_blocks = MODE == MV_GEMM_SWIGLU ? (a.n / 2) / 128 : (a.n + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (a.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   p.act = a.act; p.out_f32 = a.out_f32;
@@ -782,6 +805,29 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
 
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   int grid = device_sms() > 0 ? device_sms() : 148;
+  if (PAIR) {
+    grid &= ~1;
+    if (2 * tiles < grid) grid = 2 * tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *ta2, *tb, p);
+    if (e != cudaSuccess) {
+      set_error("gemm_bf16_tc (cta pair) launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
+    return MV_OK;
+  }
   if (tiles < grid) grid = tiles;
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
@@ -830,12 +876,19 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   MV_CHECK_ARG(!a.scale || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0, "mv_gemm_bf16: scale alignment");
   MV_CHECK_ARG(!a.shift || (reinterpret_cast<uintptr_t>(a.shift) & 15) == 0, "mv_gemm_bf16: shift alignment");
 
+  // CTA pairs (cta_group::2) for the big plain GEMMs; reserved2: 0 = auto, 1 = never, 2 = always (when legal)
+  static const int pair_env = [] { const char* e = getenv("MV_GEMM_PAIR"); return e ? atoi(e) : -1; }();  // 0 disables
+  const bool pair_legal = !a.conv && !a.colstats && a.m >= 256 && pair_env != 0;
+  const bool use_pair = pair_legal && (a.reserved2 == 2 || (a.reserved2 == 0 && a.m >= 1024 && a.n >= 512));
   switch (a.mode) {
     case MV_GEMM_SWIGLU:
       MV_CHECK_ARG(a.n % 256 == 0 && a.shift && !a.out_f32, "mv_gemm_bf16(SWIGLU): N %% 256 == 0, bias required, bf16 out");
+      // measured: the epilogue-heavy SwiGLU tile is no faster as a CTA pair (the MMA waits for both CTAs' epilogues)
+      if (pair_legal && a.reserved2 == 2) return launch_gemm<256, MV_GEMM_SWIGLU, true>(a, stream);
       return launch_gemm<256, MV_GEMM_SWIGLU>(a, stream);
     case MV_GEMM_SWIGLU_BWD:
       MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
+      if (pair_legal && a.reserved2 == 2) return launch_gemm<128, MV_GEMM_SWIGLU_BWD, true>(a, stream);
       return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
     case MV_GEMM_NN_ATOMIC:
       MV_CHECK_ARG(a.out_f32 == 1 && a.n % 8 == 0, "mv_gemm_bf16(NN_ATOMIC): fp32 output, N %% 8 == 0");
@@ -867,6 +920,7 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
           bn = waves_cost(256) <= waves_cost(128) * 1.25 ? 256 : 128;
         }
       }
+      if (use_pair && bn == 256) return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
       switch (bn) {
         case 16: return launch_gemm<16, MV_GEMM_LINEAR>(a, stream);
         case 32: return launch_gemm<32, MV_GEMM_LINEAR>(a, stream);

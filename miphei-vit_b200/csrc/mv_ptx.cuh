@@ -93,9 +93,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
 }
 // CTA-pair variant: each CTA of the pair loads into its own smem but signals the leader CTA's barrier.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  // `bar` is the CTA-local offset of the barrier; the transaction bytes are credited to the same barrier in CTA 0
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      "{\n\t.reg .b32 rb;\n\t"
+      "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [rb];\n\t}\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {

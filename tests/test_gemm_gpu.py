@@ -112,3 +112,38 @@ def test_gemm_strided_operands():
     ops.gemm(abuf, b, out=obuf[:, 256:])
     _close(obuf[:, 256:], abuf.float() @ b.float().t(), 1e-2)
     assert (obuf[:, :256] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (5264, 4608, 1552), (5264, 1536, 4096), (300, 768, 128),
+                                   (10528, 1536, 1536)])
+def test_gemm_cta_pair(M, N, K):
+    """cta_group::2 tiles (two CTAs share a 256-row tile, B halves read from the peer's smem) vs the 1-CTA kernel."""
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    b = _rand((N, K), 0.05, 2).bfloat16()
+    shift = _rand((N,), 1.0, 3)
+    resid = _rand((M, N), 1.0, 4)
+    ref = a.float() @ b.float().t() + shift + resid
+    one = ops.gemm(a, b, shift=shift, resid=resid, out_dtype=torch.float32, block_n=256, pair=1)
+    two = ops.gemm(a, b, shift=shift, resid=resid, out_dtype=torch.float32, block_n=256, pair=2)
+    _close(two, ref, 2e-5)
+    assert torch.equal(one, two)  # same accumulation order per output element
+    _close(ops.gemm(a, b, block_n=256, pair=2), a.float() @ b.float().t(), 1e-2)
+
+
+def test_gemm_cta_pair_swiglu():
+    ops = _ops()
+    M, H, K = 1500, 4096, 1536
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    w = _rand((2 * H, K), 0.03, 2).bfloat16()
+    bias = _rand((2 * H,), 0.5, 3)
+    h1 = torch.zeros((M, 2 * H), dtype=torch.bfloat16, device="cuda")
+    h2 = torch.zeros_like(h1)
+    u1 = ops.gemm(a, w, mode=ops.GEMM_SWIGLU, shift=bias, aux=h1, pair=1)
+    u2 = ops.gemm(a, w, mode=ops.GEMM_SWIGLU, shift=bias, aux=h2, pair=2)
+    assert torch.equal(u1, u2) and torch.equal(h1, h2)
+    dy = _rand((M, 1536), 1.0, 6).bfloat16()
+    w2t = _rand((H, 1536), 0.03, 7).bfloat16()
+    d1 = ops.gemm(dy, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=h1, pair=1)
+    d2 = ops.gemm(dy, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=h1, pair=2)
+    assert torch.equal(d1, d2)

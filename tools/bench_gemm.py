@@ -9,13 +9,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from miphei_vit_b200 import ops  # noqa: E402
 
 
-def bench(M, N, K, mode=0, bn=0, iters=20, compare=True):
+def bench(M, N, K, mode=0, bn=0, iters=20, compare=True, pair=0):
     nbuf = 4
     As = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
     Bs = [(torch.randn(N, K, device="cuda") * 0.05).bfloat16() for _ in range(nbuf)]
     bias = torch.randn(N, device="cuda")
     out = None
-    kw = dict(mode=mode, block_n=bn)
+    kw = dict(mode=mode, block_n=bn, pair=pair)
     if mode == ops.GEMM_SWIGLU:
         kw["shift"] = bias
     for i in range(3):
@@ -28,7 +28,7 @@ def bench(M, N, K, mode=0, bn=0, iters=20, compare=True):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    res = {"M": M, "N": N, "K": K, "mode": mode, "bn": bn, "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
+    res = {"M": M, "N": N, "K": K, "mode": mode, "bn": bn, "pair": pair, "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
     if compare and mode == 0:
         for i in range(3):
             torch.matmul(As[i % nbuf], Bs[i % nbuf].t())
@@ -44,10 +44,10 @@ def bench(M, N, K, mode=0, bn=0, iters=20, compare=True):
 
 
 if __name__ == "__main__":
-    for M in (5264, 10528, 21056):
-        for bn in (128, 256):
-            bench(M, 4608, 1536, bn=bn)
-            bench(M, 1536, 1536, bn=bn)
-            bench(M, 1536, 4096, bn=bn)
-        bench(M, 8192, 1536, mode=ops.GEMM_SWIGLU)
-        bench(M, 8192, 1536, bn=256)
+    for M in (5264, 10528):
+        for pair in (1, 2):
+            bench(M, 4608, 1552, bn=256, pair=pair, compare=(pair == 1))
+            bench(M, 1536, 1536, bn=256, pair=pair, compare=(pair == 1))
+            bench(M, 1536, 4096, bn=256, pair=pair, compare=(pair == 1))
+            bench(M, 8192, 1536, mode=ops.GEMM_SWIGLU, pair=pair)
+            bench(M, 1536, 8192, bn=256, pair=pair, compare=(pair == 1))
