@@ -360,6 +360,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       const int m = m_blk * GEMM_BLOCK_M + row_in_tile;
       const bool row_ok = m < p.m;
+      // fp32-output path: output / residual row of each of this lane's 8 row slots, and the residual of the first column
+      // chunk fetched BEFORE waiting for the accumulator (the load latency hides behind the MMAs of this tile)
+      long long orow_[8], rrow_[8];
+      float4 qn[8];
+      auto load_resid = [&](int c, float4* q) {
+        const int nn = n_blk * BLOCK_N + c * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 4 + (lane >> 3);
+          q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.resid && mm < p.m && nn < p.n) q[it] = *reinterpret_cast<const float4*>(p.resid + rrow_[it] * p.ldr + nn);
+        }
+      };
+      if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
+        if (p.out_f32) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 4 + (lane >> 3);
+            long long orow = mm, rrow = mm;
+            if (p.rows_per_group > 0) {
+              const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
+              orow = (long long)g * p.group_stride + rr + p.row_offset;
+              rrow = p.resid_row_mod ? rr : orow;
+            }
+            orow_[it] = orow;
+            rrow_[it] = rrow;
+          }
+          load_resid(0, qn);
+        }
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
@@ -373,6 +403,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
+          float4 q_[8];
+          if (p.out_f32) {  // residual of this chunk was prefetched; start fetching the next chunk's now
+#pragma unroll
+            for (int it = 0; it < 8; ++it) q_[it] = qn[it];
+            if (c + 1 < BLOCK_N / 32) load_resid(c + 1, qn);
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -387,24 +423,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
               if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
-              // all residual loads are issued before the first store: out may alias resid (in-place residual update),
-              // so the compiler cannot hoist loads over stores by itself
-              long long orow_[8], rrow_[8];
-              float4 q_[8];
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int mm = m_warp + it * 4 + (lane >> 3);
-                long long orow = mm, rrow = mm;
-                if (p.rows_per_group > 0) {
-                  const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
-                  orow = (long long)g * p.group_stride + rr + p.row_offset;
-                  rrow = p.resid_row_mod ? rr : orow;
-                }
-                orow_[it] = orow;
-                rrow_[it] = rrow;
-                q_[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.resid && mm < p.m) q_[it] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + nn);
-              }
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const int r = it * 4 + (lane >> 3);
