@@ -48,7 +48,7 @@ struct GemmDev {
 template <int BLOCK_N, int MODE = 0, bool PAIR = false>
 struct GemmCfg {
   static constexpr int kRowsB = PAIR ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by this CTA
-  static constexpr int kBoxRowsB = kRowsB < 128 ? kRowsB : 128;
+  static constexpr int kBoxRowsB = kRowsB < 128 ? kRowsB : (kRowsB % 128 == 0 ? 128 : 96);
   static constexpr int kBoxesB = kRowsB / kBoxRowsB;
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
@@ -56,7 +56,9 @@ struct GemmCfg {
   static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
   static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
-  static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+  static constexpr int kTmemRaw = 2 * BLOCK_N;
+  static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512
+                                   : kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
   static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes;
@@ -206,7 +208,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (PAIR) brow[0] = brow[cta_rank];  // leader stages the gate rows, the peer the value rows
         } else {
           brow[0] = n_blk * BLOCK_N + (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
-          brow[1] = n_blk * BLOCK_N + 128;
+          brow[1] = n_blk * BLOCK_N + Cfg::kBoxRowsB;
         }
         int cv_b = 0, cv_y = 0, cv_x = 0;
         if (p.conv && MODE != MV_GEMM_NN_ATOMIC) {  // tile rows are contiguous output pixels: m0 -> (image, y0, x0)
@@ -926,18 +928,25 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
         if (a.n <= 16) bn = 16;
         else if (a.n <= 32) bn = 32;
         else if (a.n <= 64) bn = 64;
-        else if (a.n <= 128 || a.n % 256 != 0) bn = 128;
+        else if (a.n <= 128) bn = 128;
         else {
-          // pick the tile width with the better last-wave occupancy on this problem
+          // tile width with the least (waves x width), the narrower tiles paying their lower flop/byte
           const int sms = device_sms() > 0 ? device_sms() : 148;
-          const int mb = (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-          auto waves_cost = [&](int b) {
+          const int units = use_pair ? sms / 2 : sms;
+          const int mb = use_pair ? (a.m + 255) / 256 : (a.m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+          auto cost = [&](int b, double penalty) {
             const int t = mb * ((a.n + b - 1) / b);
-            return (double)((t + sms - 1) / sms) * b;  // time ~ waves * tile width
+            return (double)((t + units - 1) / units) * b * penalty;
           };
-          bn = waves_cost(256) <= waves_cost(128) * 1.25 ? 256 : 128;
+          double best = cost(256, 1.0);
+          bn = 256;
+          if (a.n % 192 == 0 && !a.conv && !a.colstats && cost(192, 1.12) < best) { best = cost(192, 1.12); bn = 192; }
+          if (cost(128, 1.25) < best) { best = cost(128, 1.25); bn = 128; }
+          if (a.n % 256 != 0 && bn == 256 && a.n % 128 == 0 && a.n < 256) bn = 128;
         }
       }
+      if (use_pair && bn == 192) return launch_gemm<192, MV_GEMM_LINEAR, true>(a, stream);
+      if (bn == 192) return launch_gemm<192, MV_GEMM_LINEAR>(a, stream);
       if (use_pair && bn == 256) return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
       switch (bn) {
         case 16: return launch_gemm<16, MV_GEMM_LINEAR>(a, stream);

@@ -26,7 +26,8 @@ def _close(got, ref, tol):
     (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 256, 256), (128, 128, 64, 128),
     (5264, 4608, 1536, 0), (5264, 1536, 1536, 0), (5264, 1536, 4096, 0), (329, 1536, 1536, 128),
     (1000, 48, 64, 0), (777, 96, 448, 0), (640, 192, 896, 0), (300, 32, 640, 0), (300, 16, 1536, 0),
-    (2000, 64, 1600, 0), (129, 256, 1600, 256),
+    (2000, 64, 1600, 0), (129, 256, 1600, 256), (5264, 4608, 1552, 192), (700, 384, 128, 192), (3000, 1728, 256, 0),
+    (2100, 144, 32, 0),
 ])
 def test_gemm_plain(M, N, K, bn):
     ops = _ops()
@@ -129,6 +130,9 @@ def test_gemm_cta_pair(M, N, K):
     _close(two, ref, 2e-5)
     assert torch.equal(one, two)  # same accumulation order per output element
     _close(ops.gemm(a, b, block_n=256, pair=2), a.float() @ b.float().t(), 1e-2)
+    if N % 192 == 0:
+        _close(ops.gemm(a, b, block_n=192, pair=2), a.float() @ b.float().t(), 1e-2)
+        _close(ops.gemm(a, b, shift=shift, resid=resid, out_dtype=torch.float32, block_n=192, pair=2), ref, 2e-5)
 
 
 def test_gemm_cta_pair_swiglu():

@@ -45,9 +45,7 @@ def bench(M, N, K, mode=0, bn=0, iters=20, compare=True, pair=0):
 
 if __name__ == "__main__":
     for M in (5264, 10528):
-        for pair in (1, 2):
-            bench(M, 4608, 1552, bn=256, pair=pair, compare=(pair == 1))
-            bench(M, 1536, 1536, bn=256, pair=pair, compare=(pair == 1))
-            bench(M, 1536, 4096, bn=256, pair=pair, compare=(pair == 1))
-            bench(M, 8192, 1536, mode=ops.GEMM_SWIGLU, pair=pair)
-            bench(M, 1536, 8192, bn=256, pair=pair, compare=(pair == 1))
+        for bn in (256, 192, 0):
+            bench(M, 4608, 1552, bn=bn, compare=(bn == 256))
+            bench(M, 1536, 1536, bn=bn, compare=(bn == 256))
+            bench(M, 1536, 4096, bn=bn, compare=(bn == 256))

@@ -21,8 +21,11 @@ with torch.no_grad():
         blk.ls2.gamma.uniform_(0.05, 0.5)
 print("build %.1fs" % (time.time() - t0), flush=True)
 x = torch.randn(B, 3, 256, 256, device="cuda")
-for use_graphs in (False, True):
+for use_graphs, split in ((False, False), (True, False), (True, True)):
     m.engine.use_graphs = use_graphs
+    m.engine.split_streams = split
+    for w in m.engine._ws.values():
+        w.graph = None
     for _ in range(3):
         y = m.engine.infer(x, reuse_output=True)
     torch.cuda.synchronize()
@@ -35,6 +38,6 @@ for use_graphs in (False, True):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print("graphs=%s B=%d: %.3f ms/forward, %.1f tiles/s, %.1f TFLOP/s (793.4 GF/tile), launches/fwd %d" % (
-        use_graphs, B, ms, B / ms * 1e3, B * 793.4 / ms, lib.launch_count() // n), flush=True)
+    print("split=%s graphs=%s B=%d: %.3f ms/forward, %.1f tiles/s, %.1f TFLOP/s (793.4 GF/tile), launches/fwd %d" % (
+        split, use_graphs, B, ms, B / ms * 1e3, B * 793.4 / ms, lib.launch_count() // n), flush=True)
 print("finite", torch.isfinite(y).all().item(), float(y.abs().mean()))
