@@ -127,7 +127,7 @@ int mv_layernorm_bwd(const float* x, int64_t ldx, const float* w, const void* dy
                      int d, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Self-attention forward, head_dim 64, 16 <= n_tok <= 384 (timm Attention.forward -> F.scaled_dot_product_attention).
+ * Self-attention forward, head_dim 64, n_tok >= 16 (flash-style key blocks; timm Attention.forward -> F.scaled_dot_product_attention).
  *   qkv bf16 [batch*n_tok, 3*heads*64] (q | k | v per token, as nn.Linear(dim, 3*dim) lays them out),
  *   out bf16 [batch*n_tok, heads*64] token-major, lse fp32 [batch, heads, n_tok] (natural log; optional).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -1,50 +1,48 @@
-// Multi-head self-attention forward for short sequences (16 <= N <= 448 tokens, head_dim 64) on tcgen05 / TMEM.
+// Multi-head self-attention forward (head_dim 64, any sequence length >= 16) on tcgen05 / TMEM.
 //
 // Replaces timm Attention.forward's F.scaled_dot_product_attention(q, k, v) (no mask, scale 1/8, dropout 0; the ViT is
 // created at src/generators/foundation_models.py:53-57) including the reshape(B,N,3,H,64).permute(2,0,3,1,4) split
 // and the transpose(1,2).reshape(B,N,C) merge: it reads q/k/v straight from the fused qkv rows [B*N, 3*D] and writes
-// token-major O [B*N, D].
+// token-major O [B*N, D] (+ the log-sum-exp per row for the backward pass).
 //
-// Persistent kernel, one CTA per SM; work item = (image, head, 128-query tile), each CTA takes a contiguous range of
-// items so the K/V of a head are loaded once for its query tiles.  The whole key range of a head is resident, so the
-// softmax is exact and single pass (no running rescale):
-//   warp 0 (1 thread) : TMA producer — Q tiles (2 stages) and K/V (1 or 2 stages), 128-byte swizzle
-//   warp 1 (1 thread) : tcgen05.mma issuer — S = Q K^T (SS), then O = P V (A = P from TMEM, B = V MN-major from smem)
-//   warps 2..9        : softmax + epilogue, two warps per TMEM lane quadrant (each takes half of the key columns):
-//                       row max -> p = exp2((s - max) * scale*log2e) -> bf16 P written back over S in TMEM -> O / rowsum
-// TMEM: S occupies key_pad fp32 columns (P aliases its first key_pad/2), O is double buffered at columns 384 and 448.
+// Persistent kernel, one CTA per SM; work item = (image, head, 128-query tile). Keys/values stream through shared memory
+// in blocks of kb <= 128 keys with an online softmax, so any N works (329 tokens at 256 px, 1301 at 512 px).
+// A CTA runs TWO items at a time in two "slots", each with its own Q buffers, K/V ring, TMEM region and softmax
+// warpgroup; one TMA thread and one MMA thread serve both slots in a fixed interleave
+//        S_A(j+1) | PV_B(j) | S_B(j+1) | PV_A(j+1) | ...
+// so the tensor core works for one slot while the other slot's warpgroup does its exponentials:
+//   warp 0 (1 thread) : TMA producer — Q (2 buffers / slot) and K|V blocks (2 stages / slot), 128-byte swizzle
+//   warp 1 (1 thread) : tcgen05.mma issuer — S = Q K_j^T (SS), O += P V_j (A = P from TMEM, V MN-major from smem)
+//   warps 2..5 / 6..9 : softmax warpgroup of slot A / B, one query row per thread: running max with LAZY rescale of the
+//                       O accumulator (only when the max grows by > 2^8), p = exp2(s*c - m), bf16 P written over S in
+//                       TMEM, final O / l -> global.
+// TMEM per slot: S/P at +0 (kb fp32 columns, P aliases the first kb/2), O at +128 (64 columns); slots at 0 and 256.
 #include "mv_host.h"
 #include "mv_ptx.cuh"
 
 namespace mv {
 
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_MAX_KEYS = 384;   // S columns [0, 384); O buffers at 384 / 448
-constexpr int ATT_O_COL = 384;
-constexpr int ATT_MAXC = 6;         // 32-column chunks per half row (384 / 32 / 2)
+constexpr int ATT_QBYTES = 128 * 128;       // one [128 x 64] bf16 tile
+constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // log2 units
 
 struct AttnDev {
   int n_tok;     // tokens per image
-  int key_pad;   // n_tok rounded up to 16
-  int kv_box;    // key_pad / 2 rows per TMA box
+  int kb;        // keys per block (multiple of 16, <= 128)
+  int nb;        // key blocks per item
   int heads, dim;
   int q_tiles;
   int total_tiles;
-  int kv_stages;
   float scale_log2e;
-  float scale;
   __nv_bfloat16* out;
   long long ldo;
-  float* lse;  // [B, heads, n_tok] or null
+  float* lse;  // [B, heads, n_tok] or null (natural log)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -53,41 +51,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t kv_bytes = p.key_pad * 128;
-  const uint32_t sQ = smem_base;                       // 2 x 16 KB
-  const uint32_t sKV = sQ + 2 * 16384;                 // kv_stages x (K | V)
-  const uint32_t misc_off = 2 * 16384 + p.kv_stages * 2 * kv_bytes;
+  const uint32_t kv_bytes = p.kb * 128;  // one K (or V) block
+  // smem: per slot: Q[2] | KV ring [2] x (K | V, 16 KB reserved each)
+  auto sQ = [&](int slot, int buf) { return smem_base + (slot * 2 + buf) * ATT_QBYTES; };
+  auto sK = [&](int slot, int st) { return smem_base + 4 * ATT_QBYTES + ((slot * 2 + st) * 2) * ATT_QBYTES; };
+  auto sV = [&](int slot, int st) { return sK(slot, st) + ATT_QBYTES; };
+  const uint32_t misc_off = 12 * ATT_QBYTES;
   const uint32_t bar_base = smem_base + misc_off;
-  auto q_full = [&](int s) { return bar_base + 8u * s; };
-  auto q_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto kv_full = [&](int s) { return bar_base + 8u * (4 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-  const uint32_t bar_s = bar_base + 8u * 8, bar_p = bar_base + 8u * 9;
-  auto bar_o = [&](int s) { return bar_base + 8u * (10 + s); };
-  auto o_empty = [&](int s) { return bar_base + 8u * (12 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * 14;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 14);
-  float* xch_max = reinterpret_cast<float*>(smem_gen + misc_off + 128);  // [2][128]
-  float* xch_sum = xch_max + 256;                                        // [2][128]
+  // barriers per slot (11): q_full[2], q_empty[2], kv_full[2], kv_empty[2], s_full, p_full, o_full
+  auto bar = [&](int slot, int idx) { return bar_base + 8u * (slot * 11 + idx); };
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous range of work items for this CTA
   const int t0 = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
   const int t1 = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+  const int cnt = t1 - t0;
+  const int nb = p.nb;
+  // slot s handles items t0 + s, t0 + s + 2, ...
+  const int n_items[2] = {(cnt + 1) / 2, cnt / 2};
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(q_full(s), 1);
-      mbar_init(q_empty(s), 1);
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
-      mbar_init(bar_o(s), 1);
-      mbar_init(o_empty(s), 256);
+      for (int i = 0; i < 8; ++i) mbar_init(bar(s, i), 1);
+      mbar_init(bar(s, 8), 1);    // s_full
+      mbar_init(bar(s, 9), 128);  // p_full
+      mbar_init(bar(s, 10), 1);   // o_full
     }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -102,204 +94,220 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      int qs = 0, ks = 0, prev_bh = -1;
-      uint32_t qph = 0, kph = 0;
-      for (int t = t0; t < t1; ++t) {
-        const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
-        const int b = bh / p.heads, h = bh - b * p.heads;
-        const int row0 = b * p.n_tok;
-        if (bh != prev_bh) {
-          prev_bh = bh;
-          mbar_wait(kv_empty(ks), kph ^ 1);
-          const uint32_t sK = sKV + ks * 2 * kv_bytes, sV = sK + kv_bytes;
-          mbar_expect_tx(kv_full(ks), 2 * kv_bytes);
-          tma_load_2d(sK, &tmap_kv, kv_full(ks), p.dim + h * 64, row0);
-          tma_load_2d(sK + p.kv_box * 128, &tmap_kv, kv_full(ks), p.dim + h * 64, row0 + p.kv_box);
-          tma_load_2d(sV, &tmap_kv, kv_full(ks), 2 * p.dim + h * 64, row0);
-          tma_load_2d(sV + p.kv_box * 128, &tmap_kv, kv_full(ks), 2 * p.dim + h * 64, row0 + p.kv_box);
-          if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
+      const int G[2] = {n_items[0] * nb, n_items[1] * nb};
+      const int gmax = G[0] > G[1] ? G[0] : G[1];
+      for (int g = 0; g < gmax; ++g) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (g >= G[s]) continue;
+          const int it = g / nb, j = g - it * nb;
+          const int t = t0 + s + 2 * it;
+          const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
+          const int b = bh / p.heads, h = bh - b * p.heads;
+          const int row0 = b * p.n_tok;
+          if (j == 0) {
+            const int qb = it & 1;
+            mbar_wait(bar(s, 2 + qb), ((it >> 1) & 1) ^ 1);
+            mbar_expect_tx(bar(s, qb), ATT_QBYTES);
+            tma_load_2d(sQ(s, qb), &tmap_q, bar(s, qb), h * 64, row0 + qt * 128);
+          }
+          const int st = g & 1;
+          mbar_wait(bar(s, 6 + st), ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(s, 4 + st), 2 * kv_bytes);
+          tma_load_2d(sK(s, st), &tmap_kv, bar(s, 4 + st), p.dim + h * 64, row0 + j * p.kb);
+          tma_load_2d(sV(s, st), &tmap_kv, bar(s, 4 + st), 2 * p.dim + h * 64, row0 + j * p.kb);
         }
-        mbar_wait(q_empty(qs), qph ^ 1);
-        mbar_expect_tx(q_full(qs), 16384);
-        tma_load_2d(sQ + qs * 16384, &tmap_q, q_full(qs), h * 64, row0 + qt * 128);
-        if (++qs == 2) { qs = 0; qph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      int qs = 0, ks = 0, os = 0, prev_bh = -1, cur_ks = 0;
-      uint32_t qph = 0, kph = 0, oph = 0, tph = 0;
+      const int G[2] = {n_items[0] * nb, n_items[1] * nb};
+      const int gmax = G[0] > G[1] ? G[0] : G[1];
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.kb);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      const int ksteps = p.key_pad / 16;
-      for (int t = t0; t < t1; ++t) {
-        const int bh = t / p.q_tiles;
-        if (bh != prev_bh) {
-          prev_bh = bh;
-          mbar_wait(kv_full(ks), kph);
-          cur_ks = ks;
-          if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
-        }
-        const uint32_t sK = sKV + cur_ks * 2 * kv_bytes, sV = sK + kv_bytes;
-        mbar_wait(q_full(qs), qph);
+      const int ksteps = p.kb / 16;
+      auto issue_s = [&](int s, int g) {
+        const int it = g / nb, j = g - it * nb;
+        const int qb = it & 1, st = g & 1;
+        if (j == 0) mbar_wait(bar(s, qb), (it >> 1) & 1);
+        mbar_wait(bar(s, 4 + st), (g >> 1) & 1);
         tc_fence_after();
-        // ---- S = Q K^T : [128, key_pad], K = 64 (4 UMMA k-steps), keys in chunks of <= 256
-        const uint64_t dq = umma_desc_sw128(sQ + qs * 16384);
-        for (int n0 = 0; n0 < p.key_pad; n0 += 256) {
-          const int nn = p.key_pad - n0 < 256 ? p.key_pad - n0 : 256;
-          const uint32_t idesc = umma_idesc_bf16(128, nn);
-          const uint64_t dk = umma_desc_sw128(sK + n0 * 128);
+        const uint64_t dq = umma_desc_sw128(sQ(s, qb));
+        const uint64_t dk = umma_desc_sw128(sK(s, st));
+        const uint32_t d = tmem_base + s * 256;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + n0, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-        }
-        umma_commit(bar_s);
-        umma_commit(q_empty(qs));
-        // ---- O = P V : [128, 64], K = key_pad (P from TMEM, 8 columns per 16 keys; V MN-major, 2 KB per 16 keys)
-        mbar_wait(bar_p, tph);
-        mbar_wait(o_empty(os), oph ^ 1);
+        for (int k = 0; k < 4; ++k) umma_bf16(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(bar(s, 8));
+        if (j == nb - 1) umma_commit(bar(s, 2 + qb));  // Q buffer free
+      };
+      auto issue_pv = [&](int s, int g) {
+        const int it = g / nb, j = g - it * nb;
+        const int st = g & 1;
+        mbar_wait(bar(s, 9), g & 1);
         tc_fence_after();
-        const uint32_t d_o = tmem_base + ATT_O_COL + os * 64;
+        const uint32_t d = tmem_base + s * 256 + 128;
+        const uint32_t a = tmem_base + s * 256;
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t dv = umma_desc_sw128(sV + k * 2048, 1024, 1024);
-          umma_bf16_ts(d_o, tmem_base + k * 8, dv, idesc_pv, k != 0);
+          const uint64_t dv = umma_desc_sw128(sV(s, st) + k * 2048, 1024, 1024);
+          umma_bf16_ts(d, a + k * 8, dv, idesc_pv, (j | k) != 0);
         }
-        umma_commit(bar_o(os));
-        if (t + 1 == t1 || (t + 1) / p.q_tiles != bh) umma_commit(kv_empty(cur_ks));
-        if (++qs == 2) { qs = 0; qph ^= 1; }
-        if (++os == 2) { os = 0; oph ^= 1; }
-        tph ^= 1;
-      }
-    }
-  } else {
-    // ===================== softmax + epilogue =====================
-    const int sw = warp - 2;         // 0..7
-    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
-    const int half = sw >> 2;        // which half of the key columns / O columns
-    const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int n_tok = p.n_tok;
-    const int full32 = p.key_pad / 32;
-    const bool tail16 = (p.key_pad & 31) != 0;
-    const int h0 = (full32 + 1) / 2;
-    const int c_begin = half == 0 ? 0 : h0;
-    const int c_end = half == 0 ? h0 : full32;
-    const bool my_tail = tail16 && half == 1;
-    int os = 0;
-    uint32_t oph = 0, tph = 0;
-    for (int t = t0; t < t1; ++t) {
-      const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
-      const int b = bh / p.heads, h = bh - b * p.heads;
-      mbar_wait(bar_s, tph);
-      tc_fence_after();
-      // ---- pass 1: row max over this warp's columns
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= n_tok) {
+        umma_commit(bar(s, 6 + st));  // K|V stage free
+        if (j == nb - 1) umma_commit(bar(s, 10));
+      };
+      if (G[0] > 0) issue_s(0, 0);
+      if (G[1] > 0) issue_s(1, 0);
+      for (int g = 0; g < gmax; ++g) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < n_tok) mx = fmaxf(mx, __uint_as_float(v[j]));
-        }
-      }
-      if (my_tail) {
-        uint32_t v[16];
-        tmem_ld16(trow + full32 * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full32 * 32 + j < n_tok) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-      xch_max[half * 128 + r] = mx;
-      named_bar_sync(1, 256);
-      mx = fmaxf(mx, xch_max[(half ^ 1) * 128 + r]);
-      const float mxs = mx * p.scale_log2e;
-      // ---- pass 2: probabilities, kept in registers until every warp has finished reading S
-      uint32_t pk[ATT_MAXC][16];
-      uint32_t pkt[8];
-      float sum = 0.f;
-#pragma unroll
-      for (int ci = 0; ci < ATT_MAXC; ++ci) {
-        const int c = c_begin + ci;
-        if (c < c_end) {
-          uint32_t v[32];
-          tmem_ld32(trow + c * 32, v);
-          tmem_ld_wait();
-          const bool fullc = c * 32 + 32 <= n_tok;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float e0 = ex2_approx(__uint_as_float(v[2 * j]) * p.scale_log2e - mxs);
-            float e1 = ex2_approx(__uint_as_float(v[2 * j + 1]) * p.scale_log2e - mxs);
-            if (!fullc) {
-              if (c * 32 + 2 * j >= n_tok) e0 = 0.f;
-              if (c * 32 + 2 * j + 1 >= n_tok) e1 = 0.f;
-            }
-            sum += e0 + e1;
-            pk[ci][j] = pack_bf16x2(e0, e1);
+        for (int s = 0; s < 2; ++s) {
+          if (g < G[s]) {
+            issue_pv(s, g);
+            if (g + 1 < G[s]) issue_s(s, g + 1);
           }
         }
       }
-      if (my_tail) {
-        uint32_t v[16];
-        tmem_ld16(trow + full32 * 32, v);
-        tmem_ld_wait();
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int s = (warp - 2) >> 2;   // slot
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + s * 256;
+    const int n_tok = p.n_tok, kb = p.kb;
+    const int full32 = kb / 32;
+    const bool tail16 = (kb & 31) != 0;
+    const float c = p.scale_log2e;
+    int g = 0;
+    for (int it = 0; it < n_items[s]; ++it) {
+      const int t = t0 + s + 2 * it;
+      const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
+      const int b = bh / p.heads, h = bh - b * p.heads;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < nb; ++j, ++g) {
+        mbar_wait(bar(s, 8), g & 1);
+        tc_fence_after();
+        const int key0 = j * kb;
+        const bool partial = key0 + kb > n_tok;  // block holds keys beyond the sequence: mask them
+        // ---- pass 1: block row max
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < full32; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(trow + cc * 32, v);
+          tmem_ld_wait();
+          if (!partial) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = full32 * 32 + 2 * j;
-          const float e0 = col < n_tok ? ex2_approx(__uint_as_float(v[2 * j]) * p.scale_log2e - mxs) : 0.f;
-          const float e1 = col + 1 < n_tok ? ex2_approx(__uint_as_float(v[2 * j + 1]) * p.scale_log2e - mxs) : 0.f;
-          sum += e0 + e1;
-          pkt[j] = pack_bf16x2(e0, e1);
+            for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (key0 + cc * 32 + q < n_tok) mx = fmaxf(mx, __uint_as_float(v[q]));
+          }
         }
-      }
-      xch_sum[half * 128 + r] = sum;
-      named_bar_sync(2, 256);  // all reads of S are done: P may now overwrite it
+        if (tail16) {
+          uint32_t v[16];
+          tmem_ld16(trow + full32 * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int ci = 0; ci < ATT_MAXC; ++ci) {
-        const int c = c_begin + ci;
-        if (c < c_end) tmem_st16(trow + c * 16, pk[ci]);
-      }
-      if (my_tail) {
-        uint32_t z[16];
+          for (int q = 0; q < 16; ++q)
+            if (key0 + full32 * 32 + q < n_tok) mx = fmaxf(mx, __uint_as_float(v[q]));
+        }
+        const float m_new = fmaxf(m_ref, mx * c);
+        // ---- lazy rescale of the accumulator (warp-uniform decision: tcgen05.ld/st are warp collectives)
+        const bool grow = (j == 0) || (m_new - m_ref > ATT_RESCALE_THRESHOLD);
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_use = grow ? m_new : m_ref;
+          if (j > 0) {
+            const float alpha = grow ? ex2_approx(m_ref - m_new) : 1.f;
+            l *= alpha;
+            uint32_t o0[32], o1[32];
+            tmem_ld32(trow + 128, o0);
+            tmem_ld32(trow + 160, o1);
+            tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { z[j] = pkt[j]; z[8 + j] = 0u; }
-        tmem_st16(trow + full32 * 16, z);  // upper 8 columns fall beyond key_pad/2, inside the dead part of S
+            for (int q = 0; q < 32; ++q) {
+              o0[q] = __float_as_uint(__uint_as_float(o0[q]) * alpha);
+              o1[q] = __float_as_uint(__uint_as_float(o1[q]) * alpha);
+            }
+            tmem_st16(trow + 128, reinterpret_cast<uint32_t(&)[16]>(o0[0]));
+            tmem_st16(trow + 144, reinterpret_cast<uint32_t(&)[16]>(o0[16]));
+            tmem_st16(trow + 160, reinterpret_cast<uint32_t(&)[16]>(o1[0]));
+            tmem_st16(trow + 176, reinterpret_cast<uint32_t(&)[16]>(o1[16]));
+          }
+          m_ref = m_use;
+        }
+        // ---- pass 2: p = exp2(s*c - m_ref) -> bf16, written over S
+        float sum = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < full32; ++cc) {
+          uint32_t v[32], pk[16];
+          tmem_ld32(trow + cc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float e0 = ex2_approx(__uint_as_float(v[2 * q]) * c - m_ref);
+            float e1 = ex2_approx(__uint_as_float(v[2 * q + 1]) * c - m_ref);
+            if (partial) {
+              if (key0 + cc * 32 + 2 * q >= n_tok) e0 = 0.f;
+              if (key0 + cc * 32 + 2 * q + 1 >= n_tok) e1 = 0.f;
+            }
+            sum += e0 + e1;
+            pk[q] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(trow + cc * 16, pk);
+        }
+        if (tail16) {
+          uint32_t v[16], pk[16];
+          tmem_ld16(trow + full32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int key = key0 + full32 * 32 + 2 * q;
+            const float e0 = key < n_tok ? ex2_approx(__uint_as_float(v[2 * q]) * c - m_ref) : 0.f;
+            const float e1 = key + 1 < n_tok ? ex2_approx(__uint_as_float(v[2 * q + 1]) * c - m_ref) : 0.f;
+            sum += e0 + e1;
+            pk[q] = pack_bf16x2(e0, e1);
+          }
+#pragma unroll
+          for (int q = 8; q < 16; ++q) pk[q] = 0u;
+          tmem_st16(trow + full32 * 16, pk);  // upper 8 columns land beyond kb/2, inside the dead part of S
+        }
+        l += sum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar(s, 9));
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_p);
-
-      // ---- epilogue: this warp normalises and stores 32 of the 64 output columns
-      mbar_wait(bar_o(os), oph);
+      // ---- epilogue of the item: O / l -> bf16 rows
+      mbar_wait(bar(s, 10), it & 1);
       tc_fence_after();
-      const float total = sum + xch_sum[(half ^ 1) * 128 + r];
-      const float inv = 1.f / total;
-      uint32_t o[32];
-      tmem_ld32(trow + ATT_O_COL + os * 64 + half * 32, o);
+      uint32_t o0[32], o1[32];
+      tmem_ld32(trow + 128, o0);
+      tmem_ld32(trow + 160, o1);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(o_empty(os));
       const int q = qt * 128 + r;
       if (q < n_tok) {
-        __nv_bfloat16* orow = p.out + (long long)(b * n_tok + q) * p.ldo + h * 64 + half * 32;
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.out + (long long)(b * n_tok + q) * p.ldo + h * 64;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int jj = 0; jj < 4; ++jj) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[j] = u;
+          u.x = pack_bf16x2(__uint_as_float(o0[8 * jj + 0]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[jj] = u;
         }
-        if (p.lse && half == 0) p.lse[((long long)b * p.heads + h) * n_tok + q] = mx * p.scale + logf(total);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o1[8 * jj + 0]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[4 + jj] = u;
+        }
+        if (p.lse) p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l)) * 0.6931471805599453f;
       }
-      if (++os == 2) { os = 0; oph ^= 1; }
-      tph ^= 1;
     }
   }
   tc_fence_before();
@@ -317,39 +325,34 @@ extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ld
                            int heads, float scale, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(qkv && out && batch > 0 && heads > 0, "mv_attn_fwd: null/empty");
-  MV_CHECK_ARG(n_tok >= 16 && n_tok <= ATT_MAX_KEYS, "mv_attn_fwd: n_tok=%d outside [16, %d] (single-pass kernel)", n_tok,
-               ATT_MAX_KEYS);
+  MV_CHECK_ARG(n_tok >= 16, "mv_attn_fwd: n_tok=%d must be >= 16", n_tok);
   MV_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "mv_attn_fwd: out alignment");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   AttnDev p;
   p.n_tok = n_tok;
-  p.key_pad = (n_tok + 15) / 16 * 16;
-  p.kv_box = p.key_pad / 2;
+  p.nb = (n_tok + 127) / 128;
+  p.kb = ((n_tok + p.nb - 1) / p.nb + 15) / 16 * 16;  // balanced key blocks, multiple of 16, <= 128
   p.heads = heads;
   p.dim = heads * 64;
   p.q_tiles = (n_tok + 127) / 128;
   p.total_tiles = batch * heads * p.q_tiles;
-  p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
-  const int misc = 128 + 4 * 128 * 4 + 1024;
-  const int kvb = 2 * p.key_pad * 128;
-  p.kv_stages = (2 * 16384 + 2 * kvb + misc <= 227 * 1024) ? 2 : 1;
-  const int smem = 2 * 16384 + p.kv_stages * kvb + misc;
+  const int smem = 12 * ATT_QBYTES + 8 * 24 + 1024;
   const uint64_t rows = (uint64_t)batch * n_tok;
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
-  const CUtensorMap* tkv = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, p.kv_box);
+  const CUtensorMap* tkv = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, p.kb);
   if (!tq || !tkv) return MV_ERR_ARG;
-  static int smem_set = 0;
-  if (smem > smem_set) {
+  static bool attr = false;
+  if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_fwd): %s", cudaGetErrorString(e));
       return (int)e;
     }
-    smem_set = smem;
+    attr = true;
   }
   int grid = device_sms() > 0 ? device_sms() : 148;
   if (grid > p.total_tiles) grid = p.total_tiles;
