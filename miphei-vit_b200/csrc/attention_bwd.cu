@@ -11,19 +11,24 @@
 //                operands, the kernel loops over 128-query tiles and accumulates dV, dK of the block in TMEM.
 //   DKV = false: work item = (image, head, 128-query tile); Q, dO are the row operands, the loop runs over key blocks and
 //                accumulates dQ.  (S and dP are recomputed by both instances: 7 MMAs per tile pair instead of 5.)
-// Per tile pair: X = R1 C1^T and Y = R2 C2^T (SS MMAs) -> 8 softmax warps turn X into P and Y into dS (bf16, written
-// back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A operand read from TMEM and the C tiles
-// re-read from the SAME smem tiles as MN-major operands.
+// Per (128-row block, 64-column tile) pair: X = R1 C1^T and Y = R2 C2^T (SS MMAs) -> 4 warps (one row per thread) turn
+// X into P and Y into dS (bf16, written back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A
+// operand read from TMEM and the C tiles re-read from the SAME smem tiles as MN-major operands.  Two CTAs are resident per
+// SM (64 KB smem, 256 TMEM columns each), so one CTA's exponentials overlap the other CTA's MMAs.
 #include "mv_host.h"
 #include "mv_ptx.cuh"
 
 namespace mv {
 
-constexpr int ATB_THREADS = 320;
-constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
+constexpr int ATB_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 softmax-backward math (one row per thread)
+constexpr int ATB_RTILE = 128 * 128;   // bytes of one [128 x 64] bf16 row-operand tile
+constexpr int ATB_CTILE = 64 * 128;    // bytes of one [64 x 64] bf16 column-operand tile
+constexpr int ATB_TMEM = 256;          // X 64 | Y 64 | acc1 64 | acc2 64 : two CTAs per SM share the 512 columns
 
 struct AttnBwdDev {
-  int n_tok, heads, dim, blocks;  // blocks = ceil(n_tok / 128)
+  int n_tok, heads, dim;
+  int rblocks;  // ceil(n_tok / 128): outer (row) blocks
+  int cblocks;  // ceil(n_tok / 64): inner (column) blocks
   int total_items;
   float scale, scale_log2e;
   const float* lse;    // [B, heads, n_tok]
@@ -39,51 +44,56 @@ __device__ __forceinline__ float ex2a(float x) {
 }
 __device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// Two CTAs are resident per SM (64 KB smem, 256 TMEM columns, <= 170 registers each): while one CTA's warps do the
+// exponentials of a tile pair, the other CTA's MMAs own the tensor core — the overlap needs no intra-kernel ping-pong.
 template <bool DKV>
-__global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+__global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                   const __grid_constant__ CUtensorMap tmap_do,
+                                                                  const __grid_constant__ CUtensorMap tmap_qkv64,
+                                                                  const __grid_constant__ CUtensorMap tmap_do64,
                                                                   const AttnBwdDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // smem: R tiles 2 stages x (R1 | R2), C tiles 2 stages x (C1 | C2), barriers, lse/D staging
-  const uint32_t sR = smem_base, sC = smem_base + 4 * ATB_TILE;
-  const uint32_t misc_off = 8 * ATB_TILE;
+  // smem: R1 | R2 (single stage), C tiles 2 stages x (C1 | C2), barriers, lse/D staging (2 buffers)
+  const uint32_t sR = smem_base, sC = smem_base + 2 * ATB_RTILE;
+  const uint32_t misc_off = 2 * ATB_RTILE + 4 * ATB_CTILE;
   const uint32_t bar_base = smem_base + misc_off;
-  auto r_full = [&](int s) { return bar_base + 8u * s; };
-  auto r_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto c_full = [&](int s) { return bar_base + 8u * (4 + s); };
-  auto c_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-  const uint32_t bar_xy = bar_base + 8u * 8, bar_pd = bar_base + 8u * 9, bar_acc = bar_base + 8u * 10,
-                 acc_empty = bar_base + 8u * 11;
-  const uint32_t tmem_slot = bar_base + 8u * 12;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 12);
-  float* s_lse = reinterpret_cast<float*>(smem_gen + misc_off + 128);  // [128] (scaled by log2e)
-  float* s_dsum = s_lse + 128;                                          // [128]
+  const uint32_t r_full = bar_base, r_empty = bar_base + 8;
+  auto c_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto c_empty = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t bar_xy = bar_base + 8u * 6, bar_pd = bar_base + 8u * 7, bar_acc = bar_base + 8u * 8,
+                 acc_empty = bar_base + 8u * 9;
+  const uint32_t tmem_slot = bar_base + 8u * 10;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 10);
+  float* s_lse = reinterpret_cast<float*>(smem_gen + misc_off + 128);  // [2][64] (scaled by log2e)
+  float* s_dsum = s_lse + 128;                                          // [2][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = (int)((long long)p.total_items * blockIdx.x / gridDim.x);
   const int t1 = (int)((long long)p.total_items * (blockIdx.x + 1) / gridDim.x);
-  const int nblk = p.blocks;
-  constexpr uint32_t COL_X = 0, COL_Y = 128, COL_A1 = 256, COL_A2 = 320;
+  const int nrb = p.rblocks, ncb = p.cblocks;
+  constexpr uint32_t COL_X = 0, COL_Y = 64, COL_A1 = 128, COL_A2 = 192;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_qkv64);
+    tma_prefetch_desc(&tmap_do64);
+    mbar_init(r_full, 1);
+    mbar_init(r_empty, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(r_full(s), 1);
-      mbar_init(r_empty(s), 1);
       mbar_init(c_full(s), 1);
       mbar_init(c_empty(s), 1);
     }
     mbar_init(bar_xy, 1);
-    mbar_init(bar_pd, 256);
+    mbar_init(bar_pd, 128);
     mbar_init(bar_acc, 1);
-    mbar_init(acc_empty, 256);
+    mbar_init(acc_empty, 128);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, ATB_TMEM);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -94,33 +104,32 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      int rs = 0, cs = 0;
+      int cs = 0;
       uint32_t rph = 0, cph = 0;
       for (int t = t0; t < t1; ++t) {
-        const int bh = t / nblk, ob = t - bh * nblk;  // outer block: key block (DKV) or query tile
+        const int bh = t / nrb, ob = t - bh * nrb;  // outer block: 128 keys (DKV) or 128 queries
         const int b = bh / p.heads, h = bh - b * p.heads;
         const int row0 = b * p.n_tok;
-        mbar_wait(r_empty(rs), rph ^ 1);
-        mbar_expect_tx(r_full(rs), 2 * ATB_TILE);
-        const uint32_t r1 = sR + rs * 2 * ATB_TILE, r2 = r1 + ATB_TILE;
+        mbar_wait(r_empty, rph ^ 1);
+        mbar_expect_tx(r_full, 2 * ATB_RTILE);
         if (DKV) {
-          tma_load_2d(r1, &tmap_qkv, r_full(rs), p.dim + h * 64, row0 + ob * 128);      // K_j
-          tma_load_2d(r2, &tmap_qkv, r_full(rs), 2 * p.dim + h * 64, row0 + ob * 128);  // V_j
+          tma_load_2d(sR, &tmap_qkv, r_full, p.dim + h * 64, row0 + ob * 128);                  // K_j
+          tma_load_2d(sR + ATB_RTILE, &tmap_qkv, r_full, 2 * p.dim + h * 64, row0 + ob * 128);  // V_j
         } else {
-          tma_load_2d(r1, &tmap_qkv, r_full(rs), h * 64, row0 + ob * 128);              // Q_i
-          tma_load_2d(r2, &tmap_do, r_full(rs), h * 64, row0 + ob * 128);               // dO_i
+          tma_load_2d(sR, &tmap_qkv, r_full, h * 64, row0 + ob * 128);                          // Q_i
+          tma_load_2d(sR + ATB_RTILE, &tmap_do, r_full, h * 64, row0 + ob * 128);               // dO_i
         }
-        if (++rs == 2) { rs = 0; rph ^= 1; }
-        for (int ib = 0; ib < nblk; ++ib) {
+        rph ^= 1;
+        for (int ib = 0; ib < ncb; ++ib) {
           mbar_wait(c_empty(cs), cph ^ 1);
-          mbar_expect_tx(c_full(cs), 2 * ATB_TILE);
-          const uint32_t c1 = sC + cs * 2 * ATB_TILE, c2 = c1 + ATB_TILE;
+          mbar_expect_tx(c_full(cs), 2 * ATB_CTILE);
+          const uint32_t c1 = sC + cs * 2 * ATB_CTILE, c2 = c1 + ATB_CTILE;
           if (DKV) {
-            tma_load_2d(c1, &tmap_qkv, c_full(cs), h * 64, row0 + ib * 128);            // Q_i
-            tma_load_2d(c2, &tmap_do, c_full(cs), h * 64, row0 + ib * 128);             // dO_i
+            tma_load_2d(c1, &tmap_qkv64, c_full(cs), h * 64, row0 + ib * 64);            // Q (64 queries)
+            tma_load_2d(c2, &tmap_do64, c_full(cs), h * 64, row0 + ib * 64);             // dO
           } else {
-            tma_load_2d(c1, &tmap_qkv, c_full(cs), p.dim + h * 64, row0 + ib * 128);      // K_j
-            tma_load_2d(c2, &tmap_qkv, c_full(cs), 2 * p.dim + h * 64, row0 + ib * 128);  // V_j
+            tma_load_2d(c1, &tmap_qkv64, c_full(cs), p.dim + h * 64, row0 + ib * 64);      // K (64 keys)
+            tma_load_2d(c2, &tmap_qkv64, c_full(cs), 2 * p.dim + h * 64, row0 + ib * 64);  // V
           }
           if (++cs == 2) { cs = 0; cph ^= 1; }
         }
@@ -129,18 +138,17 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      int rs = 0, cs = 0;
+      int cs = 0;
       uint32_t rph = 0, cph = 0, xph = 0, aph = 0;
-      const uint32_t idesc_xy = umma_idesc_bf16(128, 128);
+      const uint32_t idesc_xy = umma_idesc_bf16(128, 64);
       const uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
       for (int t = t0; t < t1; ++t) {
-        mbar_wait(r_full(rs), rph);
-        const uint32_t r1 = sR + rs * 2 * ATB_TILE, r2 = r1 + ATB_TILE;
-        const uint64_t dr1 = umma_desc_sw128(r1), dr2 = umma_desc_sw128(r2);
-        for (int ib = 0; ib < nblk; ++ib) {
+        mbar_wait(r_full, rph);
+        const uint64_t dr1 = umma_desc_sw128(sR), dr2 = umma_desc_sw128(sR + ATB_RTILE);
+        for (int ib = 0; ib < ncb; ++ib) {
           mbar_wait(c_full(cs), cph);
           tc_fence_after();
-          const uint32_t c1 = sC + cs * 2 * ATB_TILE, c2 = c1 + ATB_TILE;
+          const uint32_t c1 = sC + cs * 2 * ATB_CTILE, c2 = c1 + ATB_CTILE;
           const uint64_t dc1 = umma_desc_sw128(c1), dc2 = umma_desc_sw128(c2);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_X, dr1 + 2 * k, dc1 + 2 * k, idesc_xy, k != 0);
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
           if (ib == 0) mbar_wait(acc_empty, aph ^ 1);  // previous item's accumulators drained
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile
             if (DKV) {
               const uint64_t dmn2 = umma_desc_sw128(c2 + k * 2048, 1024, 1024);
               umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + k * 8, dmn2, idesc_acc, (ib | k) != 0);
@@ -160,29 +168,28 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
             umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + k * 8, dmn1, idesc_acc, (ib | k) != 0);
           }
           umma_commit(c_empty(cs));
-          if (ib == nblk - 1) {
+          if (ib == ncb - 1) {
             umma_commit(bar_acc);
-            umma_commit(r_empty(rs));
+            umma_commit(r_empty);
           }
           if (++cs == 2) { cs = 0; cph ^= 1; }
           xph ^= 1;
         }
-        if (++rs == 2) { rs = 0; rph ^= 1; }
+        rph ^= 1;
         aph ^= 1;
       }
     }
   } else {
-    // ===================== softmax-backward math + epilogue (8 warps) =====================
-    const int sw = warp - 2;
+    // ===================== softmax-backward math + epilogue (4 warps, thread = row) =====================
     const int quad = warp & 3;
-    const int half = sw >> 2;
     const int r = quad * 32 + lane;
-    const int tid = sw * 32 + lane;  // 0..255
+    const int tid = threadIdx.x - 64;  // 0..127
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n_tok = p.n_tok;
     uint32_t xph = 0, aph = 0;
+    int itn = 0;
     for (int t = t0; t < t1; ++t) {
-      const int bh = t / nblk, ob = t - bh * nblk;
+      const int bh = t / nrb, ob = t - bh * nrb;
       const int b = bh / p.heads, h = bh - b * p.heads;
       const long long vec0 = (long long)bh * n_tok;
       const int orow = ob * 128 + r;  // key (DKV) or query index of this thread's row
@@ -191,37 +198,34 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
         lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
         dsum_r = p.dsum[vec0 + orow];
       }
-      for (int ib = 0; ib < nblk; ++ib) {
-        if (DKV) {  // per-column (query) statistics of this inner tile
-          if (tid < 128) {
-            const int q = ib * 128 + tid;
-            s_lse[tid] = q < n_tok ? p.lse[vec0 + q] * 1.4426950408889634f : 0.f;
-          } else {
-            const int q = ib * 128 + tid - 128;
-            s_dsum[tid - 128] = q < n_tok ? p.dsum[vec0 + q] : 0.f;
-          }
-          nbar(1, 256);
+      for (int ib = 0; ib < ncb; ++ib, ++itn) {
+        const float* sl = s_lse + (itn & 1) * 64;
+        const float* sd = s_dsum + (itn & 1) * 64;
+        if (DKV) {  // per-column (query) statistics of this inner tile, double buffered
+          const int q = ib * 64 + (tid & 63);
+          if (tid < 64) s_lse[(itn & 1) * 64 + tid] = q < n_tok ? p.lse[vec0 + q] * 1.4426950408889634f : 0.f;
+          else s_dsum[(itn & 1) * 64 + tid - 64] = q < n_tok ? p.dsum[vec0 + q] : 0.f;
+          nbar(1, 128);
         }
         mbar_wait(bar_xy, xph);
         tc_fence_after();
         uint32_t pp[2][16], pd[2][16];
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          const int c0 = half * 64 + ci * 32;
           uint32_t x[32], y[32];
-          tmem_ld32(trow + COL_X + c0, x);
-          tmem_ld32(trow + COL_Y + c0, y);
+          tmem_ld32(trow + COL_X + ci * 32, x);
+          tmem_ld32(trow + COL_Y + ci * 32, y);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float pv[2], dv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = c0 + 2 * j + e;
-              const int icol = ib * 128 + col;
+              const int col = ci * 32 + 2 * j + e;
+              const int icol = ib * 64 + col;
               const bool ok = orow < n_tok && icol < n_tok;
-              const float l2 = DKV ? s_lse[col] : lse_r;
-              const float dd = DKV ? s_dsum[col] : dsum_r;
+              const float l2 = DKV ? sl[col] : lse_r;
+              const float dd = DKV ? sd[col] : dsum_r;
               const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
               pv[e] = pr;
               dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd) * p.scale;
@@ -230,12 +234,11 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
             pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
           }
         }
-        nbar(2, 256);  // every warp has finished reading X / Y: P and dS may overwrite them
+        // every column of this row has been read (this warp is the only reader of its lanes): P / dS overwrite X / Y
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          const int pc = half * 32 + ci * 16;
-          if (DKV) tmem_st16(trow + COL_X + pc, pp[ci]);
-          tmem_st16(trow + COL_Y + pc, pd[ci]);
+          if (DKV) tmem_st16(trow + COL_X + ci * 16, pp[ci]);
+          tmem_st16(trow + COL_Y + ci * 16, pd[ci]);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -245,41 +248,40 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
       // ---- epilogue: accumulators -> bf16 rows of dqkv
       mbar_wait(bar_acc, aph);
       tc_fence_after();
-      uint32_t a0[32], a1[32];
-      int col_base;
-      if (DKV) {  // half 0 stores dV (acc1), half 1 stores dK (acc2); 64 columns each
-        const uint32_t src = half == 0 ? COL_A1 : COL_A2;
-        tmem_ld32(trow + src, a0);
-        tmem_ld32(trow + src + 32, a1);
-        col_base = (half == 0 ? 2 * p.dim : p.dim) + h * 64;
-      } else {    // dQ: half 0 stores columns 0..31, half 1 columns 32..63
-        tmem_ld32(trow + COL_A2 + half * 32, a0);
-        col_base = h * 64 + half * 32;
+      uint32_t a0[32], a1[32], b0[32], b1[32];
+      tmem_ld32(trow + COL_A2, a0);
+      tmem_ld32(trow + COL_A2 + 32, a1);
+      if (DKV) {
+        tmem_ld32(trow + COL_A1, b0);
+        tmem_ld32(trow + COL_A1 + 32, b1);
       }
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty);
       if (orow < n_tok) {
-        __nv_bfloat16* dst = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + col_base;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(a0[8 * j + 0]), __uint_as_float(a0[8 * j + 1]));
-          u.y = pack_bf16x2(__uint_as_float(a0[8 * j + 2]), __uint_as_float(a0[8 * j + 3]));
-          u.z = pack_bf16x2(__uint_as_float(a0[8 * j + 4]), __uint_as_float(a0[8 * j + 5]));
-          u.w = pack_bf16x2(__uint_as_float(a0[8 * j + 6]), __uint_as_float(a0[8 * j + 7]));
-          reinterpret_cast<uint4*>(dst)[j] = u;
-        }
-        if (DKV) {
+        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + h * 64;
+        auto store64 = [&](__nv_bfloat16* dst, const uint32_t* lo, const uint32_t* hi) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(a1[8 * j + 0]), __uint_as_float(a1[8 * j + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a1[8 * j + 2]), __uint_as_float(a1[8 * j + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a1[8 * j + 4]), __uint_as_float(a1[8 * j + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a1[8 * j + 6]), __uint_as_float(a1[8 * j + 7]));
-            reinterpret_cast<uint4*>(dst)[4 + j] = u;
+            u.x = pack_bf16x2(__uint_as_float(lo[8 * j + 0]), __uint_as_float(lo[8 * j + 1]));
+            u.y = pack_bf16x2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3]));
+            u.z = pack_bf16x2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5]));
+            u.w = pack_bf16x2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7]));
+            reinterpret_cast<uint4*>(dst)[j] = u;
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(hi[8 * j + 0]), __uint_as_float(hi[8 * j + 1]));
+            w.y = pack_bf16x2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3]));
+            w.z = pack_bf16x2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5]));
+            w.w = pack_bf16x2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7]));
+            reinterpret_cast<uint4*>(dst)[4 + j] = w;
           }
+        };
+        if (DKV) {
+          store64(base + p.dim, a0, a1);      // dK  (acc2 = dS^T Q)
+          store64(base + 2 * p.dim, b0, b1);  // dV  (acc1 = P^T dO)
+        } else {
+          store64(base, a0, a1);              // dQ  (acc2 = dS K)
         }
       }
       aph ^= 1;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attn_bwd_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, ATB_TMEM);
   }
 }
 
@@ -345,8 +347,9 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   p.n_tok = n_tok;
   p.heads = heads;
   p.dim = heads * 64;
-  p.blocks = (n_tok + 127) / 128;
-  p.total_items = batch * heads * p.blocks;
+  p.rblocks = (n_tok + 127) / 128;
+  p.cblocks = (n_tok + 63) / 64;
+  p.total_items = batch * heads * p.rblocks;
   p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.lse = lse;
@@ -355,8 +358,10 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   p.lddqkv = lddqkv;
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
   const CUtensorMap* td = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 128);
-  if (!tq || !td) return MV_ERR_ARG;
-  const int smem = 8 * ATB_TILE + 128 + 2 * 128 * 4 + 1024;
+  const CUtensorMap* tq64 = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 64);
+  const CUtensorMap* td64 = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 64);
+  if (!tq || !td || !tq64 || !td64) return MV_ERR_ARG;
+  const int smem = 2 * ATB_RTILE + 4 * ATB_CTILE + 128 + 4 * 64 * 4 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -367,11 +372,11 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
     }
     attr = true;
   }
-  int grid = device_sms() > 0 ? device_sms() : 148;
+  int grid = 2 * (device_sms() > 0 ? device_sms() : 148);  // two co-resident CTAs per SM
   if (grid > p.total_items) grid = p.total_items;
-  attn_bwd_kernel<true><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, p);
+  attn_bwd_kernel<true><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, *tq64, *td64, p);
   MV_CHECK_LAUNCH("attn_bwd_dkv");
-  attn_bwd_kernel<false><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, p);
+  attn_bwd_kernel<false><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, *tq64, *td64, p);
   MV_CHECK_LAUNCH("attn_bwd_dq");
   return MV_OK;
 }
