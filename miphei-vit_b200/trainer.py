@@ -26,6 +26,48 @@ def lr_lambda(step, total_steps, warmup_steps=400):
     return max(0.0, 1.0 - (step - half) / (total_steps - half))
 
 
+def shard_tiles(n_tiles, rank, world):
+    """Round-robin tile assignment of a whole-slide sweep (independent units, no collective)."""
+    return range(rank, n_tiles, world)
+
+
+class FlatParams:
+    """Every trainable parameter as a view of ONE flat fp32 buffer, decoder segment first, with a matching flat gradient
+    buffer (p.grad views) and two contiguous all-reduce buckets. Device-agnostic (tested on CPU with gloo)."""
+
+    def __init__(self, model, device=None):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        dec = [(n, p) for n, p in named if n.startswith("decoder.")]
+        lora = [(n, p) for n, p in named if not n.startswith("decoder.")]
+        self.order = dec + lora
+        dev = device if device is not None else named[0][1].device
+        pad = lambda n: (n + 3) // 4 * 4  # noqa: E731  (16-byte aligned segments)
+        self.n_dec = sum(pad(p.numel()) for _, p in dec)
+        self.total = self.n_dec + sum(pad(p.numel()) for _, p in lora)
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for _, p in self.order:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().float().flatten())
+                p.data = self.flat[off:off + n].view(p.shape)
+                p.grad = self.gflat[off:off + n].view(p.shape)
+                off += pad(n)
+
+    def bucket(self, i):
+        return self.gflat[:self.n_dec] if i == 0 else self.gflat[self.n_dec:]
+
+    def allreduce_bucket(self, i, async_op=True):
+        """Average one bucket over the ranks (NCCL supports AVG natively; gloo gets SUM + scale)."""
+        b = self.bucket(i)
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(b, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=False)
+        b.div_(dist.get_world_size())
+        return w
+
+
 class Trainer:
     def __init__(self, model, marker_weights=None, base_lr=None, batch_size=None, total_steps=10000, warmup_steps=400,
                  lambda_factor=50.0, loss_mode=ops.LOSS_WMSE, betas=(0.5, 0.999), eps=1e-7, max_norm=1.0):
@@ -40,26 +82,12 @@ class Trainer:
         self.betas, self.eps, self.max_norm = betas, eps, max_norm
         self.marker_weights = marker_weights.to(dev).float().contiguous() if marker_weights is not None else None
         self.step_count = 0
-        # ---- flatten: [decoder | lora]
-        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-        dec = [(n, p) for n, p in named if n.startswith("decoder.")]
-        lora = [(n, p) for n, p in named if not n.startswith("decoder.")]
-        self.order = dec + lora
-        pad = lambda n: (n + 3) // 4 * 4  # noqa: E731  (16-byte aligned segments)
-        self.n_dec = sum(pad(p.numel()) for _, p in dec)
-        total = self.n_dec + sum(pad(p.numel()) for _, p in lora)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.fp = FlatParams(model, dev)
+        self.order, self.n_dec = self.fp.order, self.fp.n_dec
+        self.flat, self.gflat = self.fp.flat, self.fp.gflat
+        total = self.fp.total
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        with torch.no_grad():
-            for _, p in self.order:
-                n = p.numel()
-                self.flat[off:off + n].copy_(p.detach().float().flatten())
-                p.data = self.flat[off:off + n].view(p.shape)
-                p.grad = self.gflat[off:off + n].view(p.shape)
-                off += pad(n)
         self.norm = torch.zeros(2, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -75,7 +103,7 @@ class Trainer:
             return
         self.comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
-            self._dec_work = dist.all_reduce(self.gflat[:self.n_dec], op=dist.ReduceOp.AVG, async_op=True)
+            self._dec_work = self.fp.allreduce_bucket(0, async_op=True)
 
     def current_lr(self):
         return self.base_lr * lr_lambda(self.step_count, self.total_steps, self.warmup_steps)
@@ -93,7 +121,7 @@ class Trainer:
                 self._dec_work.wait()
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
                 self._dec_work = None
-            dist.all_reduce(self.gflat[self.n_dec:], op=dist.ReduceOp.AVG)
+            self.fp.allreduce_bucket(1, async_op=False)
         ops.grad_norm(self.gflat, self.max_norm, norm_out=self.norm, workspace=self.norm_ws)
         self.step_count += 1
         lr = self.base_lr * lr_lambda(self.step_count - 1, self.total_steps, self.warmup_steps)
