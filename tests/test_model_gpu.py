@@ -84,3 +84,39 @@ def test_cpu_input_fails_loudly():
         model(torch.zeros(1, 3, 128, 128))
     with pytest.raises(AssertionError):
         model(torch.zeros(1, 3, 256, 256, device="cuda"))
+
+
+def test_512px_three_channel_geometry_hemit_style():
+    """BASELINE configs[3] geometry: 512-px tiles (36x36 + 5 = 1301 tokens, flash attention over 11 key blocks), 3 output
+    channels; reduced width / depth so the CPU oracle stays fast. Eval forward + one training step."""
+    from miphei_vit_b200 import ops
+    from miphei_vit_b200.trainer import Trainer
+
+    cfg = om.Config(img_size=512, embed_dim=128, depth=2, num_heads=2, hidden=256, out_chans=3)
+    sd = om.init_state_dict(cfg, seed=9, perturb=True)
+    x = om.normalize_tiles(om.synthetic_tiles_u8(2, cfg.img_size, seed=3))
+    y = om.synthetic_targets(2, cfg.out_chans, cfg.img_size, seed=4)
+    with torch.no_grad():
+        ref = om.miphei_forward(sd, x, cfg, training=False)
+    model = build(cfg, sd)
+    with torch.no_grad():
+        got = model(x.cuda())
+    check_pred(got, ref)
+    # training step vs oracle
+    osd = {k: v.clone() for k, v in sd.items()}
+    keys = om.trainable_keys(osd)
+    for k in keys:
+        osd[k].requires_grad_(True)
+    w = torch.ones(3)
+    rp = om.miphei_forward(osd, x, cfg, training=True)
+    rl = om.weighted_mse_loss(y, rp, w, 50.0)
+    gref = dict(zip(keys, torch.autograd.grad(rl, [osd[k] for k in keys])))
+    model.train()
+    tr = Trainer(model, marker_weights=w, batch_size=2, total_steps=100)
+    pred = model(x.cuda())
+    loss, dpred = ops.loss_fwd_bwd(pred.detach().float().contiguous(), y.cuda(), tr.marker_weights, lambda_factor=50.0)
+    pred.backward(dpred)
+    got_g = {n: p.grad.detach().float().cpu() for n, p in tr.order}
+    c = om.cosine(torch.cat([got_g[k].flatten() for k in keys]), torch.cat([gref[k].flatten() for k in keys]))
+    assert abs(loss.item() - rl.item()) < 2e-2 * rl.item()
+    assert c >= 0.999, c
