@@ -45,7 +45,8 @@ struct GemmDev {
 
 // PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
 // the B rows (the tensor core reads the other half from the peer's shared memory), halving B traffic per SM.
-template <int BLOCK_N, int MODE = 0, bool PAIR = false>
+// LIGHT: shallow smem ring so that TWO CTAs fit on an SM (epilogue-bound problems: K of one or two blocks, or narrow N)
+template <int BLOCK_N, int MODE = 0, bool PAIR = false, bool LIGHT = false>
 struct GemmCfg {
   static constexpr int kRowsB = PAIR ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by this CTA
   static constexpr int kBoxRowsB = kRowsB < 128 ? kRowsB : (kRowsB % 128 == 0 ? 128 : 96);
@@ -53,7 +54,8 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
+  static constexpr int kStagesDeep = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
+  static constexpr int kStages = !LIGHT ? kStagesDeep : (BLOCK_N <= 32 ? 4 : BLOCK_N <= 64 ? 3 : 2);
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
   static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
   static constexpr int kTmemRaw = 2 * BLOCK_N;
@@ -134,12 +136,13 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BLOCK_N, int MODE, bool PAIR = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
+__global__ void __launch_bounds__(GEMM_THREADS, LIGHT ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
-  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
   constexpr int STAGES = Cfg::kStages;
+  static_assert(!LIGHT || (2 * Cfg::kTmemCols <= 512 && !PAIR), "two resident CTAs must share the 512 TMEM columns");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int tile_start = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -618,16 +621,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const float* w2 = reinterpret_cast<const float*>(p.in2);
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
 #pragma unroll 1
-        for (int hd = 0; hd < heads; ++hd) {
+        for (int hl = 0; hl < BLOCK_N / 16; ++hl) {
+          const int hd = n_blk * (BLOCK_N / 16) + hl;
+          if (hd >= heads) break;  // warp-uniform
           uint32_t v[16];
-          tmem_ld16(taddr + hd * 16, v);
+          tmem_ld16(taddr + hl * 16, v);
           tmem_ld_wait();
           float acc = __ldg(p.resid + hd);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = hd * 16 + j;
-            const float a = fmaxf(__uint_as_float(v[j]) * __ldg(p.scale + n) + __ldg(p.shift + n), 0.f);
-            acc += a * __ldg(w2 + n);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int n = hd * 16 + j4 * 4;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + n));
+            acc += fmaxf(__uint_as_float(v[j4 * 4 + 0]) * sc.x + sh.x, 0.f) * ww.x;
+            acc += fmaxf(__uint_as_float(v[j4 * 4 + 1]) * sc.y + sh.y, 0.f) * ww.y;
+            acc += fmaxf(__uint_as_float(v[j4 * 4 + 2]) * sc.z + sh.z, 0.f) * ww.z;
+            acc += fmaxf(__uint_as_float(v[j4 * 4 + 3]) * sc.w + sh.w, 0.f) * ww.w;
           }
           if (row_ok) o[hd] = __float2bfloat16(1.f / (1.f + __expf(-acc)));
         }
@@ -641,24 +651,44 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        // three taps per round: their TMEM loads and the neighbour-gate loads are all in flight before the first use
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t v[16];
-          tmem_ld16(taddr + tap * 16, v);
+        for (int t3 = 0; t3 < 3; ++t3) {
+          uint32_t v[3][16];
+          uint4 g0[3], g1[3];
+          bool inb[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int tap = t3 * 3 + q;
+            tmem_ld16(taddr + tap * 16, v[q]);
+            const int yy = py + t3 - 1, xx = px + q - 1;
+            inb[q] = yy >= 0 && yy < p.conv_h && xx >= 0 && xx < p.conv_w;
+            g0[q] = make_uint4(0, 0, 0, 0);
+            g1[q] = g0[q];
+            if (inb[q]) {
+              const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.in2) +
+                                        ((long long)bimg * hw + (long long)yy * p.conv_w + xx) * p.ldin2;
+              if (p.ldin2 == 16) {
+                g0[q] = *reinterpret_cast<const uint4*>(gp);
+                g1[q] = *reinterpret_cast<const uint4*>(gp + 8);
+              } else {
+                __nv_bfloat16 tmp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tmp[j] = j < p.n ? gp[j] : __float2bfloat16(0.f);
+                g0[q] = *reinterpret_cast<const uint4*>(tmp);
+                g1[q] = *reinterpret_cast<const uint4*>(tmp + 8);
+              }
+            }
+          }
           tmem_ld_wait();
-          const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-          if (yy >= 0 && yy < p.conv_h && xx >= 0 && xx < p.conv_w) {
-            const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.in2) + ((long long)bimg * hw + (long long)yy * p.conv_w + xx) * p.ldin2;
-            if (p.ldin2 == 16) {
-              float g[16];
-              load_bf16x8(gp, g);
-              load_bf16x8(gp + 8, g + 8);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] += g[j] * __uint_as_float(v[j]);
-            } else {
+          for (int q = 0; q < 3; ++q) {
+            const uint32_t gu[8] = {g0[q].x, g0[q].y, g0[q].z, g0[q].w, g1[q].x, g1[q].y, g1[q].z, g1[q].w};
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < p.n) acc[j] += __bfloat162float(gp[j]) * __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) {
+              const float2 gf = unpack_bf16x2(gu[j]);
+              acc[2 * j] += gf.x * __uint_as_float(v[q][2 * j]);
+              acc[2 * j + 1] += gf.y * __uint_as_float(v[q][2 * j + 1]);
             }
           }
         }
@@ -752,11 +782,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ------------------------------------------------------------------ host launch
-template <int BLOCK_N, int MODE, bool PAIR = false>
+template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
 static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE, PAIR>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE, PAIR, LIGHT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -848,6 +878,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
     return MV_OK;
   }
+  if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
   if (tiles < grid) grid = tiles;
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
@@ -921,7 +952,8 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
     case MV_GEMM_HEAD_GATE:
       MV_CHECK_ARG(a.n % 16 == 0 && a.n <= 256 && a.scale && a.shift && a.in2 && a.resid && !a.out_f32,
                    "mv_gemm_bf16(HEAD_GATE): N = 16*heads <= 256; scale, shift, in2 (w2) and resid (b2) required");
-      return launch_gemm<256, MV_GEMM_HEAD_GATE>(a, stream);
+      MV_CHECK_ARG((reinterpret_cast<uintptr_t>(a.in2) & 15) == 0, "mv_gemm_bf16(HEAD_GATE): w2 alignment");
+      return launch_gemm<128, MV_GEMM_HEAD_GATE, false, true>(a, stream);
     case MV_GEMM_LINEAR: {
       int bn = a.block_n;
       if (bn == 0) {
@@ -943,6 +975,17 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
           if (a.n % 192 == 0 && !a.conv && !a.colstats && cost(192, 1.12) < best) { best = cost(192, 1.12); bn = 192; }
           if (cost(128, 1.25) < best) { best = cost(128, 1.25); bn = 128; }
           if (a.n % 256 != 0 && bn == 256 && a.n % 128 == 0 && a.n < 256) bn = 128;
+        }
+      }
+      {
+        // epilogue-bound shapes (one or two K blocks, or a narrow N over many rows): two CTAs per SM
+        const int kblocks = (a.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+        const long long tiles128 = (long long)((a.m + 127) / 128) * ((a.n + 127) / 128);
+        const bool many = tiles128 >= 2ll * (device_sms() > 0 ? device_sms() : 148);
+        if (a.block_n == 0 && many && !use_pair) {
+          if (kblocks <= 2 && a.n >= 128) return launch_gemm<128, MV_GEMM_LINEAR, false, true>(a, stream);
+          if (bn == 64) return launch_gemm<64, MV_GEMM_LINEAR, false, true>(a, stream);
+          if (bn == 32) return launch_gemm<32, MV_GEMM_LINEAR, false, true>(a, stream);
         }
       }
       if (use_pair && bn == 192) return launch_gemm<192, MV_GEMM_LINEAR, true>(a, stream);
