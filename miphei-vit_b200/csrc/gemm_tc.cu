@@ -17,6 +17,10 @@ namespace mv {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
+// the SwiGLU epilogues (exp per element, extra loads / stores) need twice the epilogue warps to keep up with the MMAs:
+// two warps per TMEM lane quadrant, each taking every other 32-column chunk
+__host__ __device__ constexpr int gemm_epi_warps(int mode) { return (mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD) ? 8 : 4; }
+__host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * gemm_epi_warps(mode); }
 
 struct GemmDev {
   int m, n, k;
@@ -54,14 +58,16 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesDeep = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
+  static constexpr int kEpiWarps = gemm_epi_warps(MODE);
+  static constexpr int kRingBudget = (kEpiWarps == 8 ? 177 : 196) * 1024;  // leave room for the larger staging area
+  static constexpr int kStagesDeep = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kStages = !LIGHT ? kStagesDeep : (BLOCK_N <= 32 ? 4 : BLOCK_N <= 64 ? 3 : 2);
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
   static constexpr int kAccStride = MODE == MV_GEMM_HEAD_CONV ? 256 : BLOCK_N;
   static constexpr int kTmemRaw = 2 * BLOCK_N;
   static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512
                                    : kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
@@ -137,7 +143,7 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 
 // ------------------------------------------------------------------ kernel
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
-__global__ void __launch_bounds__(GEMM_THREADS, LIGHT ? 2 : 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), LIGHT ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
@@ -162,7 +168,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* staging_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::kStageBytes + 256);
-  float* cstat = staging_all + 4 * 32 * 36;  // [2][BLOCK_N]
+  float* cstat = staging_all + Cfg::kEpiWarps * 32 * 36;  // [2][BLOCK_N]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -176,7 +182,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), PAIR ? 8 : 4);  // one arrival per epilogue warp (pair: the peer's warps arrive remotely)
+      // one arrival per epilogue warp (pair: the peer's warps arrive remotely)
+      mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * Cfg::kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -336,8 +343,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
     const int quad = warp & 3;
+    const int ew = warp - 2;           // epilogue warp index
+    const int egrp = ew >> 2;          // which share of the column chunks (only with 8 epilogue warps)
+    constexpr int EGRPS = Cfg::kEpiWarps / 4;
     const int row_in_tile = quad * 32 + lane;
-    const int ep_tid = threadIdx.x - 64;  // 0..127
+    const int ep_tid = threadIdx.x - 64;  // 0..127 (4-warp modes)
     int as = 0;
     uint32_t aphase = 0;
     int stat_nblk = -1;
@@ -554,7 +564,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // tile columns [0,128) = gate, [128,256) = value for hidden units n_blk*128 ..; silu(g)*v is formed per thread,
         // then transposed through smem so that every output row segment is written contiguously
         const int half = p.n / 2;
-        float* stg = staging_all + quad * (32 * 36);
+        float* stg = staging_all + ew * (32 * 36);
         const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
         auto stage_and_store = [&](const float* f32vals, __nv_bfloat16* dst, long long ld, int col0) {
 #pragma unroll
@@ -577,7 +587,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
         };
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = egrp; c < 4; c += EGRPS) {
           uint32_t g[32], u[32];
           tmem_ld32(taddr + c * 32, g);
           tmem_ld32(taddr + 128 + c * 32, u);
@@ -709,10 +719,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       } else {  // MV_GEMM_SWIGLU_BWD: acc = dU tile (128 hidden units); N == H
         const int H = p.n;
-        float* stg = staging_all + quad * (32 * 36);
+        float* stg = staging_all + ew * (32 * 36);
         const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = egrp; c < BLOCK_N / 32; c += EGRPS) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -860,7 +870,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     if (2 * tiles < grid) grid = 2 * tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(MODE));
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -880,7 +890,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   }
   if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
+  kern<<<grid, gemm_threads(MODE), Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
 }
