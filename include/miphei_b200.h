@@ -205,6 +205,16 @@ int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* 
 int mv_bn_finalize(const float* colstats, double count, const float* gamma, const float* beta, const float* pre_bias,
                    float* running_mean, float* running_var, float momentum, float eps, int c, float* scale, float* shift,
                    float* mean, float* rstd, void* stream);
+/* Closed-form train-mode BatchNorm statistics of the SegmentationHead gates (AttentionBlock.psi[0..1],
+ * src/generators/unet.py:407-422): the BN input W1 f + b1 is linear in the 32-channel map f, so its batch mean / variance
+ * follow from E[f] and E[f f^T] (csrc/heads_stats.cu).
+ *   mv_gram32             gram (fp32 [40, 32], zeroed by the caller): rows 0..31 += f^T f, row 32 += 1^T f; f bf16 [m, 32]
+ *   mv_heads_bn_from_gram (gram, count = m) -> folded (scale, shift) for relu(scale * (W1 f) + shift), saved batch
+ *                         (mean, rstd) of W1 f + b1, running-stat update; w1 fp32 [c, 32] = the weights the gate GEMM uses */
+int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, void* stream);
+int mv_heads_bn_from_gram(const float* gram, double count, const float* w1, const float* b1, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, float momentum, float eps, int c,
+                          float* scale, float* shift, float* mean, float* rstd, void* stream);
 int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int64_t m, int c,
                      void* stream);
 int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, int z_f32, const float* mean, const float* rstd,

@@ -1,0 +1,196 @@
+// Train-mode BatchNorm statistics of the 16 SegmentationHead gates (AttentionBlock.psi[0..1], src/generators/unet.py:
+// 407-422) in closed form.  The BatchNorm input of hidden unit j is a_j = W1_j . f + b1_j, a LINEAR function of the
+// 32-channel full-resolution map f, so its batch statistics follow from the first two moments of f:
+//
+//   mean_j = W1_j . E[f] + b1_j            var_j = W1_j Cov(f) W1_j^T,   Cov(f) = E[f f^T] - E[f] E[f]^T
+//
+// mv_gram32 reads f once (64 B / pixel) and accumulates  G = f^T f  [32, 32]  and  1^T f  [32]  on the warp-level tensor
+// cores (mma.sync m16n8k16, fp32 accumulate) — instead of materialising / reducing a [pixels, 256] activation map.
+// mv_heads_bn_from_gram turns (G, 1^T f) into the folded (scale, shift) of the gate kernel, the saved (mean, rstd) and the
+// running-statistics update (torch.nn.BatchNorm2d semantics: momentum, unbiased variance).
+#include "mv_host.h"
+#include "mv_ptx.cuh"
+
+namespace mv {
+
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_CHUNK = 64;     // pixels per warp iteration
+constexpr int GRAM_PITCH = 40;     // bf16 elements per staged pixel row (80 B: conflict-free ldmatrix rows)
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// gram: fp32 [40, 32], pre-zeroed; rows 0..31 += f^T f, row 32 += 1^T f  (the layout the heads backward consumes)
+__global__ void __launch_bounds__(GRAM_THREADS) gram32_kernel(const __nv_bfloat16* __restrict__ f, long long ldf, long long M,
+                                                              float* __restrict__ gram) {
+  __shared__ __align__(16) __nv_bfloat16 stage[GRAM_THREADS / 32][GRAM_CHUNK * GRAM_PITCH];
+  __shared__ float red[33 * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 33 * 32; i += GRAM_THREADS) red[i] = 0.f;
+  __syncthreads();
+  __nv_bfloat16* st = stage[warp];
+  const uint32_t st_addr = smem_u32(st);
+  // acc[mt][nt][4]: channels 16*mt + {g, g+8} x channels 8*nt + 2t + {0,1}
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  float csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = 0.f;
+
+  const long long nchunks = (M + GRAM_CHUNK - 1) / GRAM_CHUNK;
+  const long long wid = (long long)blockIdx.x * (GRAM_THREADS / 32) + warp;
+  const long long wstep = (long long)gridDim.x * (GRAM_THREADS / 32);
+  const int seg = lane & 3;   // 16-byte segment (8 channels) of a pixel row
+  const int prow = lane >> 2; // pixel within a group of 8
+  for (long long ch = wid; ch < nchunks; ch += wstep) {
+    const long long p0 = ch * GRAM_CHUNK;
+    uint4 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long p = p0 + it * 8 + prow;
+      v[it] = make_uint4(0, 0, 0, 0);
+      if (p < M) v[it] = *reinterpret_cast<const uint4*>(f + p * ldf + seg * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      *reinterpret_cast<uint4*>(st + (it * 8 + prow) * GRAM_PITCH + seg * 8) = v[it];
+      const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16x2(w[j]);
+        csum[2 * j] += x.x;
+        csum[2 * j + 1] += x.y;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int ks = 0; ks < GRAM_CHUNK / 16; ++ks) {
+      // transposed 8x8 loads of the staged [pixel][channel] tile: matrix q = (pixels 8*(q>>1).., channels 8*(q&1)..)
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int q = lane >> 3;
+        const int row = ks * 16 + (lane & 7) + 8 * (q >> 1);
+        const int col = mt * 16 + 8 * (q & 1);
+        ldmatrix_x4_trans(st_addr + (row * GRAM_PITCH + col) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+      }
+      // the B fragment of channel block nt (k = pixel, n = channel) is the same data: regs {0, 2} of the A tile holding
+      // channels 8*nt.. (even nt) or regs {1, 3} (odd nt)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          mma_bf16_16816(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], a[nt >> 1][nt & 1], a[nt >> 1][2 + (nt & 1)]);
+    }
+    __syncwarp();
+  }
+  // fold the warps of this CTA in shared memory, then one global atomic per entry per CTA
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r0 = mt * 16 + g, c0 = nt * 8 + 2 * t;
+      atomicAdd(&red[r0 * 32 + c0], acc[mt][nt][0]);
+      atomicAdd(&red[r0 * 32 + c0 + 1], acc[mt][nt][1]);
+      atomicAdd(&red[(r0 + 8) * 32 + c0], acc[mt][nt][2]);
+      atomicAdd(&red[(r0 + 8) * 32 + c0 + 1], acc[mt][nt][3]);
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float s = csum[j];
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    if (lane < 4) atomicAdd(&red[32 * 32 + seg * 8 + j], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 33 * 32; i += GRAM_THREADS) {
+    const float x = red[i];
+    if (x != 0.f) atomicAdd(gram + i, x);
+  }
+}
+
+// one thread per hidden unit j; all moment arithmetic in double (256 x 32 x 32 multiply-adds in total)
+__global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double count, const float* __restrict__ w1,
+                                          const float* __restrict__ b1, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float* __restrict__ running_mean,
+                                          float* __restrict__ running_var, float momentum, float eps, int C,
+                                          float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                          float* __restrict__ rstd_out) {
+  __shared__ double cov[32 * 32];
+  __shared__ double mf[32];
+  if (threadIdx.x < 32) mf[threadIdx.x] = (double)gram[32 * 32 + threadIdx.x] / count;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) cov[i] = (double)gram[i] / count - mf[i >> 5] * mf[i & 31];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= C) return;
+  double w[32];
+#pragma unroll
+  for (int a = 0; a < 32; ++a) w[a] = (double)w1[j * 32 + a];
+  double lin = 0.0, var = 0.0;
+#pragma unroll 4
+  for (int a = 0; a < 32; ++a) {
+    lin += w[a] * mf[a];
+    double r = 0.0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) r += cov[a * 32 + b] * w[b];
+    var += w[a] * r;
+  }
+  if (var < 0.0) var = 0.0;
+  const double mean = lin + (double)b1[j];  // statistics of (W1 f + b1); the gate GEMM applies (scale, shift) to W1 f
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[j] * rstd;
+  scale[j] = sc;
+  shift[j] = beta[j] - (float)lin * sc;
+  mean_out[j] = (float)mean;
+  rstd_out[j] = rstd;
+  if (running_mean) {
+    running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * (float)mean;
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
+  }
+}
+
+}  // namespace mv
+
+extern "C" int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(f && gram && m > 0, "mv_gram32: null/empty");
+  MV_CHECK_ARG(ldf >= 32 && ldf % 8 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "mv_gram32: rows of 32 bf16, 16-byte aligned");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long nchunks = (m + GRAM_CHUNK - 1) / GRAM_CHUNK;
+  const int sms = device_sms() > 0 ? device_sms() : 148;
+  long long grid = (nchunks + (GRAM_THREADS / 32) - 1) / (GRAM_THREADS / 32);
+  if (grid > 4ll * sms) grid = 4ll * sms;
+  gram32_kernel<<<(unsigned)grid, GRAM_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
+  MV_CHECK_LAUNCH("gram32");
+  return MV_OK;
+}
+
+extern "C" int mv_heads_bn_from_gram(const float* gram, double count, const float* w1, const float* b1, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                     int c, float* scale, float* shift, float* mean, float* rstd, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(gram && w1 && b1 && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0,
+               "mv_heads_bn_from_gram: null/empty");
+  MV_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "mv_heads_bn_from_gram: running stats go together");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  heads_bn_from_gram_kernel<<<(c + 63) / 64, 64, 0, stream>>>(gram, count, w1, b1, gamma, beta, running_mean, running_var,
+                                                             momentum, eps, c, scale, shift, mean, rstd);
+  MV_CHECK_LAUNCH("heads_bn_from_gram");
+  return MV_OK;
+}

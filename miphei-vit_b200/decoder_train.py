@@ -79,6 +79,7 @@ class DecoderTrain:
             w1p = torch.zeros((256, 64), device=dev)
             w1p[:, :32] = W1
             self.gate_w = w1p.to(torch.bfloat16)
+            self.W1r = self.gate_w[:, :32].float().contiguous()      # the bf16-rounded weights the gate GEMM multiplies by
             self.conv_w = packing.pack_conv3x3(W3, [32])            # [16, 576] for HEAD_CONV
             w3t = W3.permute(2, 3, 0, 1).reshape(144, 32)            # row tap*16 + h, col c
             self.W3t = w3t
@@ -148,11 +149,11 @@ class DecoderTrain:
         f2 = f.view(M, 32)
         self.f, self.f2, self.Bn, self.S, self.M = f, f2, Bn, S, M
         # heads: statistics pass, then the two fused inference kernels with the batch-statistic fold
-        stats = self._buf("hd.stats", (2, 256), torch.float32)
-        stats.zero_()
-        ops.gemm(f2, self.gate_w[:, :32], shift=self.b1, colstats=stats, no_out=True)
+        # batch statistics of the 256 gate units in closed form from the moments of f (E[f], E[f f^T]): one 64 B/pixel pass
+        FF = self._buf("hd.FF", (40, 32), torch.float32)
+        ops.gram32(f2, out=FF)                                          # rows 0..31 = f^T f, row 32 = 1^T f
         fin = self._buf("hd.fin", (4, 256), torch.float32)
-        ops.bn_finalize(stats, M, self.gam, self.bet, self.rm_cat, self.rv_cat, pre_bias=self.b1, out=fin)
+        ops.heads_bn_from_gram(FF, M, self.W1r, self.b1, self.gam, self.bet, self.rm_cat, self.rv_cat, out=fin)
         for hd in self.heads:
             hd[0].psi[1].num_batches_tracked += 1
         self.hfin = fin
@@ -232,9 +233,7 @@ class DecoderTrain:
         E = self._buf("hd.E", (40, 256), torch.float32)
         E.zero_()
         ops.gemm(fTm, e, mode=ops.GEMM_NN_ATOMIC, out=E)               # rows 0..31 = f^T e, row 32 = 1^T e
-        FF = self._buf("hd.FF", (40, 32), torch.float32)
-        FF.zero_()
-        ops.gemm(fTm, f2, mode=ops.GEMM_NN_ATOMIC, out=FF)              # rows 0..31 = f^T f, row 32 = 1^T f
+        FF = self._buf("hd.FF", (40, 32), torch.float32)                # f^T f / 1^T f, computed by the forward pass
         # small fp32 algebra ([256, 32]-sized) — closed-form BatchNorm / gate / 1x1-conv gradients
         W1, b1, gam, w2 = self.W1, self.b1, self.gam, self.w2
         EF, E1 = E[:32].t(), E[32]

@@ -76,6 +76,11 @@ class MipheiEngine:
         self.direct_grad_sink = False          # trainer mode: backward writes into p.grad (flat buffer views) directly
         self.decoder_train = None
         self._dec_train_versions = None
+        # eval: fold the rank-8 LoRA updates into the q / v rows of the QKV weight at pack time,
+        # W' = W + alpha * (A B)^T (src/generators/lora.py:29-33 computes x W^T + alpha (x A) B — the same linear map),
+        # which removes the x @ [A_q | A_v] GEMM and the 16 extra K columns from every block of the frozen forward
+        self.merge_lora_eval = True
+        self._merged_versions = None
 
     # ------------------------------------------------------------------ geometry
     def _geometry(self):
@@ -101,6 +106,7 @@ class MipheiEngine:
         self._bwd_packed = False
         self._lora_bwd_versions = None
         self._dec_train_versions = None
+        self._merged_versions = None
 
     def _train_tape(self, B):
         tape = self._tapes.get(B)
@@ -170,6 +176,20 @@ class MipheiEngine:
                 pb["wqkv_ext"][:D, D:D + 8] = (lq.alpha * lq.B.detach()).t()
                 pb["wqkv_ext"][2 * D:, D + 8:D + 16] = (lv.alpha * lv.B.detach()).t()
 
+    def _pack_lora_merged(self):
+        """Eval-only QKV weight with the LoRA updates folded in (fp32 sum, one bf16 rounding)."""
+        D = self.D
+        with torch.no_grad():
+            for blk, pb in zip(self.model.encoder.vit.blocks, self.blocks):
+                lq, lv = pb["lora"]
+                w = blk.attn.qkv.qkv.weight.detach().float().clone()
+                w[:D] += lq.alpha * (lq.A.detach().float() @ lq.B.detach().float()).t()
+                w[2 * D:] += lv.alpha * (lv.A.detach().float() @ lv.B.detach().float()).t()
+                if "wqkv_m" in pb:
+                    pb["wqkv_m"].copy_(w)  # same address: cached TMA descriptors / captured graphs stay valid
+                else:
+                    pb["wqkv_m"] = w.to(torch.bfloat16)
+
     def _pack_trainable(self):
         """Decoder weights for the eval path (BatchNorm folded with running statistics)."""
         dec = self.model.decoder
@@ -204,6 +224,9 @@ class MipheiEngine:
         if self._lora_versions != ver:
             self._pack_lora()
             self._lora_versions = ver
+        if not train and self.merge_lora_eval and self._merged_versions != ver:
+            self._pack_lora_merged()
+            self._merged_versions = ver
         if not train and self._train_versions != ver:
             self._pack_trainable()
             for ws in self._ws.values():
@@ -228,10 +251,14 @@ class MipheiEngine:
         xn = ws.xn_ext[:, :D]
         xt = ws.xn_ext[:, D:D + 16]
         xe = ws.xn_ext[:, :D + 16]
+        merged = self.merge_lora_eval
         for pb in self.blocks:
             ops.layernorm_fwd(ws.x, pb["n1w"], pb["n1b"], out=xn)
-            ops.gemm(xn, pb["acat"], out=xt)
-            ops.gemm(xe, pb["wqkv_ext"][:, :D + 16], shift=pb["bqkv"], out=ws.qkv)
+            if merged:
+                ops.gemm(xn, pb["wqkv_m"], shift=pb["bqkv"], out=ws.qkv)
+            else:
+                ops.gemm(xn, pb["acat"], out=xt)
+                ops.gemm(xe, pb["wqkv_ext"][:, :D + 16], shift=pb["bqkv"], out=ws.qkv)
             ops.attn_fwd(ws.qkv, B, N, self.heads, out=ws.o)
             ops.gemm(ws.o, pb["wproj"], scale=pb["g1"], shift=pb["g1b"], resid=ws.x, out=ws.x)
             ops.layernorm_fwd(ws.x, pb["n2w"], pb["n2b"], out=ws.xn2)

@@ -65,6 +65,9 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_i64, c_void_p]),
     "mv_bn_finalize": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv_gram32": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
+    "mv_heads_bn_from_gram": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mv_bn_relu_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "mv_bn_relu_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_i64, c_int, c_void_p]),

@@ -312,6 +312,33 @@ def bn_finalize(colstats, count, gamma, beta, running_mean, running_var, pre_bia
     return out
 
 
+def gram32(f, out=None):
+    """out (fp32 [40, 32], zeroed here): rows 0..31 = f^T f, row 32 = 1^T f for f bf16 [M, 32] (mv_gram32)."""
+    lib = _lib_for(f)
+    _rowmajor(f, "f")
+    assert f.dtype == torch.bfloat16 and f.shape[1] == 32
+    if out is None:
+        out = torch.zeros((40, 32), dtype=torch.float32, device=f.device)
+    else:
+        out.zero_()
+    _lib.check(lib.mv_gram32(_ptr(f), f.stride(0), f.shape[0], _ptr(out), _stream()), "mv_gram32")
+    return out
+
+
+def heads_bn_from_gram(gram, count, w1, b1, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, out=None):
+    """closed-form BatchNorm batch statistics of W1 f + b1 from the moments of f (mv_heads_bn_from_gram)."""
+    lib = _lib_for(gram)
+    C = gamma.numel()
+    assert w1.dtype == torch.float32 and w1.is_contiguous() and w1.shape == (C, 32)
+    if out is None:
+        out = torch.empty((4, C), dtype=torch.float32, device=gram.device)
+    _lib.check(lib.mv_heads_bn_from_gram(_ptr(gram), float(count), _ptr(w1), _ptr(b1), _ptr(gamma), _ptr(beta),
+                                         _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), C,
+                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
+               "mv_heads_bn_from_gram")
+    return out
+
+
 def bn_relu_apply(z, scale, shift, out=None):
     lib = _lib_for(z)
     M, C = z.shape

@@ -77,6 +77,38 @@ def test_infer_full_size_matches_oracle():
     assert half.dtype == torch.float16
 
 
+def test_lora_folded_into_qkv_matches_explicit_lora_path():
+    """Eval folds alpha * (A B)^T into the q / v weight rows (engine.merge_lora_eval); the explicit x @ A path (the one the
+    training forward uses) must give the same predictions, and a LoRA update must be picked up by the folded weights."""
+    cfg = om.Config(img_size=128, embed_dim=128, depth=2, num_heads=2, hidden=256, out_chans=3)
+    sd = om.init_state_dict(cfg, seed=5, perturb=True)
+    model = build(cfg, sd)
+    x = om.normalize_tiles(om.synthetic_tiles_u8(2, cfg.img_size, seed=6)).cuda()
+    with torch.no_grad():
+        ref = om.miphei_forward(sd, x.cpu(), cfg, training=False)
+        assert model.engine.merge_lora_eval
+        folded = model(x).float().cpu()
+        model.engine.merge_lora_eval = False
+        for ws in model.engine._ws.values():
+            ws.graph = None
+        explicit = model(x).float().cpu()
+        model.engine.merge_lora_eval = True
+        for ws in model.engine._ws.values():
+            ws.graph = None
+    check_pred(folded, ref)
+    check_pred(explicit, ref)
+    assert om.pearson(folded, explicit) >= 0.9999
+    with torch.no_grad():
+        for blk in model.encoder.vit.blocks:
+            blk.attn.qkv.lora_q.B.mul_(-3.0)
+            blk.attn.qkv.lora_v.B.mul_(-3.0)
+        sd2 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        ref2 = om.miphei_forward(sd2, x.cpu(), cfg, training=False)
+        got2 = model(x).float().cpu()
+    check_pred(got2, ref2)
+    assert not torch.allclose(got2, folded)
+
+
 def test_cpu_input_fails_loudly():
     cfg = om.Config(img_size=128, embed_dim=128, depth=1, num_heads=2, hidden=256, out_chans=2)
     model = build(cfg, om.init_state_dict(cfg, seed=1))

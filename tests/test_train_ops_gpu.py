@@ -120,3 +120,36 @@ def test_clip_and_adam_match_torch():
         assert abs(nc[0].item() - ref_norm.item()) < 1e-4 * ref_norm.item()
         ops.adam_clip_step(p, g, m, v, nc, step, 8e-4)
         assert (p - p_ref.detach()).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("M", [64, 1000, 65536 + 37])
+def test_gram32_and_closed_form_head_batchnorm(M):
+    """mv_gram32 / mv_heads_bn_from_gram against torch: moments of f, then train-mode BatchNorm2d statistics of the
+    1x1-conv gate units W1 f + b1 (AttentionBlock.psi[0..1], src/generators/unet.py:407-422)."""
+    ops = _ops()
+    f = (_rand((M, 32), 1.0, 3).relu() + 0.1).bfloat16()  # post-ReLU map: non-negative, non-zero mean
+    gram = ops.gram32(f)
+    fd = f.double()
+    ref_g = fd.t() @ fd
+    assert torch.allclose(gram[:32].double(), ref_g, rtol=2e-4, atol=1e-3 * M ** 0.5)
+    assert torch.allclose(gram[32].double(), fd.sum(0), rtol=2e-4, atol=1e-3)
+    assert float(gram[33:].abs().max()) == 0.0
+    C = 48
+    w1 = _rand((C, 32), 0.05, 4).bfloat16().float().contiguous()
+    b1, gamma, beta = _rand((C,), 0.1, 5), _rand((C,), 0.2, 6) + 1.0, _rand((C,), 0.1, 7)
+    bn = torch.nn.BatchNorm2d(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    a = (f.float() @ w1.t() + b1).t().reshape(1, C, M, 1)
+    y_ref = bn(a)
+    fin = ops.heads_bn_from_gram(gram, M, w1, b1, gamma, beta, rm, rv, momentum=bn.momentum, eps=bn.eps)
+    y = (f.float() @ w1.t()) * fin[0] + fin[1]  # folded (scale, shift) act on W1 f
+    assert torch.allclose(y.t().reshape(1, C, M, 1), y_ref, rtol=1e-3, atol=2e-3)
+    assert torch.allclose(fin[2], a.mean((0, 2, 3)), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(fin[3], (a.var((0, 2, 3), unbiased=False) + bn.eps).rsqrt(), rtol=1e-3)
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv, bn.running_var, rtol=1e-3, atol=1e-5)
