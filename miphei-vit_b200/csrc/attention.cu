@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_sync();  // PDL: prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -356,7 +357,7 @@ extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ld
   }
   int grid = device_sms() > 0 ? device_sms() : 148;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  attn_fwd_kernel<<<grid, ATT_THREADS, smem, stream>>>(*tq, *tkv, p);
+  MV_LAUNCH(attn_fwd_kernel, grid, ATT_THREADS, smem, stream, *tq, *tkv, p);
   MV_CHECK_LAUNCH("attn_fwd");
   return MV_OK;
 }

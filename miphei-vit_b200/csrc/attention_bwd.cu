@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_sync();  // PDL: prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo,
                                      const __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ dsum,
                                      int batch, int n_tok, int heads) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)batch * n_tok) return;
@@ -339,7 +341,7 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   MV_CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0, "mv_attn_bwd: leading dimensions must be multiples of 8");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long rows = (long long)batch * n_tok;
-  attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
+  MV_LAUNCH(attn_bwd_prep_kernel, (unsigned)((rows + 7) / 8), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dout), lddo, reinterpret_cast<const __nv_bfloat16*>(out), ldo, dsum, batch,
       n_tok, heads);
   MV_CHECK_LAUNCH("attn_bwd_prep");
@@ -374,9 +376,9 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   }
   int grid = 2 * (device_sms() > 0 ? device_sms() : 148);  // two co-resident CTAs per SM
   if (grid > p.total_items) grid = p.total_items;
-  attn_bwd_kernel<true><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, *tq64, *td64, p);
+  MV_LAUNCH((attn_bwd_kernel<true>), grid, ATB_THREADS, smem, stream, *tq, *td, *tq64, *td64, p);
   MV_CHECK_LAUNCH("attn_bwd_dkv");
-  attn_bwd_kernel<false><<<grid, ATB_THREADS, smem, stream>>>(*tq, *td, *tq64, *td64, p);
+  MV_LAUNCH((attn_bwd_kernel<false>), grid, ATB_THREADS, smem, stream, *tq, *td, *tq64, *td64, p);
   MV_CHECK_LAUNCH("attn_bwd_dq");
   return MV_OK;
 }

@@ -17,6 +17,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ colstats, float cou
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = colstats[c] / count;
@@ -53,6 +54,7 @@ __device__ __forceinline__ void load_z8(const void* z, long long i, float* f) {
 template <bool ZF32>
 __global__ void bn_relu_apply_kernel(const void* __restrict__ z, const float* __restrict__ scale,
                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long M, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * cg) return;
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(BNB_THREADS) bn_relu_bwd_stats_kernel(
     const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
     const void* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ sums, long long M, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   extern __shared__ float red[];  // [2][256][8]
   const int cg = C / 8;
   const int cgi = threadIdx.x % cg;
@@ -131,6 +134,7 @@ __global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, l
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ sums, float inv_n,
                                          __nv_bfloat16* __restrict__ dz, long long M, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * cg) return;
@@ -167,7 +171,7 @@ extern "C" int mv_bn_finalize(const float* colstats, double count, const float* 
   MV_CHECK_ARG(colstats && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "mv_bn_finalize: null/empty");
   MV_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "mv_bn_finalize: running stats go together");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(colstats, (float)count, gamma, beta, pre_bias, running_mean,
+  MV_LAUNCH(bn_finalize_kernel, (c + 127) / 128, 128, 0, stream, colstats, (float)count, gamma, beta, pre_bias, running_mean,
                                                           running_var, momentum, eps, c, scale, shift, mean, rstd);
   MV_CHECK_LAUNCH("bn_finalize");
   return MV_OK;
@@ -179,9 +183,9 @@ extern "C" int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, co
   MV_CHECK_ARG(z && scale && shift && y && m > 0 && c % 8 == 0, "mv_bn_relu_apply: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = m * (c / 8);
-  if (z_f32) bn_relu_apply_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  if (z_f32) MV_LAUNCH((bn_relu_apply_kernel<true>), (unsigned)((total + 255) / 256), 256, 0, stream, 
       z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
-  else bn_relu_apply_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  else MV_LAUNCH((bn_relu_apply_kernel<false>), (unsigned)((total + 255) / 256), 256, 0, stream, 
       z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
   MV_CHECK_LAUNCH("bn_relu_apply");
   return MV_OK;
@@ -202,16 +206,16 @@ extern "C" int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const
   }
   const int smem = 2 * BNB_THREADS * 8 * 4;
   const unsigned sgrid = (unsigned)((m + BNB_ROWS - 1) / BNB_ROWS);
-  if (z_f32) bn_relu_bwd_stats_kernel<true><<<sgrid, BNB_THREADS, smem, stream>>>(
+  if (z_f32) MV_LAUNCH((bn_relu_bwd_stats_kernel<true>), sgrid, BNB_THREADS, smem, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, sums, m, c);
-  else bn_relu_bwd_stats_kernel<false><<<sgrid, BNB_THREADS, smem, stream>>>(
+  else MV_LAUNCH((bn_relu_bwd_stats_kernel<false>), sgrid, BNB_THREADS, smem, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, sums, m, c);
   MV_CHECK_LAUNCH("bn_relu_bwd_stats");
   const long long total = m * (c / 8);
-  if (z_f32) bn_relu_bwd_apply_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  if (z_f32) MV_LAUNCH((bn_relu_bwd_apply_kernel<true>), (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, gamma, sums,
       (float)(1.0 / (double)m), reinterpret_cast<__nv_bfloat16*>(dz), m, c);
-  else bn_relu_bwd_apply_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  else MV_LAUNCH((bn_relu_bwd_apply_kernel<false>), (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), z, mean, rstd, gamma, sums,
       (float)(1.0 / (double)m), reinterpret_cast<__nv_bfloat16*>(dz), m, c);
   MV_CHECK_LAUNCH("bn_relu_bwd_apply");

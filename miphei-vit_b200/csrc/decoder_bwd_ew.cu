@@ -16,6 +16,7 @@ namespace mv {
 // in [M, C] (pitch ldi) -> out [R, ldo] with out[c, m] = in[m, c]; optional extra row C filled with ones.
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out,
                                       long long ldo, long long M, int C, int ones_row) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ __nv_bfloat16 tile[64][66];
   const long long m0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
@@ -52,6 +53,7 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
 // dup [B, 2h, 2w, C] (pitch ldu per pixel) -> dx [B, h, w, C]; one thread per (input pixel, 8 channels)
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dup, long long ldu, __nv_bfloat16* __restrict__ dx,
                                       int B, int h, int w, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long total = (long long)B * h * w * cg;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +97,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dup, lon
 // u [B, 2h, 2w, C]: u[2y, 2x] = dz[y, x], zero elsewhere
 __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ u, int B, int h,
                                      int w, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long total = (long long)B * 4 * h * w * cg;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +115,7 @@ __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ dz, __nv_
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
                                 long long ldb, __nv_bfloat16* __restrict__ out, long long M, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * cg) return;
@@ -133,6 +137,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long l
 __global__ void __launch_bounds__(256) heads_ds_kernel(const float* __restrict__ dpred, const float* __restrict__ pred,
                                                        __nv_bfloat16* __restrict__ ds, float* __restrict__ dbias, int heads,
                                                        int hw) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float sh[8];
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(128) heads_bwd_stencil_kernel(const __nv_bfloa
                                                                 __nv_bfloat16* __restrict__ dt,
                                                                 __nv_bfloat16* __restrict__ du, float* __restrict__ db2,
                                                                 int H, int W, long long M) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float sh[4][16];
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool ok = m < M;
@@ -248,7 +254,7 @@ extern "C" int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t
   MV_CHECK_ARG(in && out && m > 0 && c > 0 && c % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0 && ldo >= m, "mv_transpose_bf16: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   dim3 grid((unsigned)((m + 63) / 64), (c + 63) / 64), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldi,
+  MV_LAUNCH(transpose_bf16_kernel, grid, block, 0, stream, reinterpret_cast<const __nv_bfloat16*>(in), ldi,
                                                     reinterpret_cast<__nv_bfloat16*>(out), ldo, m, c, ones_row);
   MV_CHECK_LAUNCH("transpose_bf16");
   return MV_OK;
@@ -259,7 +265,7 @@ extern "C" int mv_upsample2x_bwd(const void* dup, int64_t ldu, void* dx, int bat
   MV_CHECK_ARG(dup && dx && batch > 0 && c % 8 == 0 && ldu % 8 == 0, "mv_upsample2x_bwd: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)batch * h * w * (c / 8);
-  upsample2x_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  MV_LAUNCH(upsample2x_bwd_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dup), ldu, reinterpret_cast<__nv_bfloat16*>(dx), batch, h, w, c);
   MV_CHECK_LAUNCH("upsample2x_bwd");
   return MV_OK;
@@ -270,7 +276,7 @@ extern "C" int mv_zero_insert2x(const void* dz, void* u, int batch, int h, int w
   MV_CHECK_ARG(dz && u && batch > 0 && c % 8 == 0, "mv_zero_insert2x: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)batch * 4 * h * w * (c / 8);
-  zero_insert2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  MV_LAUNCH(zero_insert2x_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<__nv_bfloat16*>(u), batch, h, w, c);
   MV_CHECK_LAUNCH("zero_insert2x");
   return MV_OK;
@@ -282,7 +288,7 @@ extern "C" int mv_add_bf16(const void* a, int64_t lda, const void* b, int64_t ld
   MV_CHECK_ARG(a && b && out && m > 0 && c % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "mv_add_bf16: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = m * (c / 8);
-  add_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  MV_LAUNCH(add_bf16_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(a), lda, reinterpret_cast<const __nv_bfloat16*>(b), ldb,
       reinterpret_cast<__nv_bfloat16*>(out), m, c);
   MV_CHECK_LAUNCH("add_bf16");
@@ -296,7 +302,7 @@ extern "C" int mv_heads_ds(const float* dpred, const float* pred, void* ds, floa
   MV_CHECK_ARG(dpred && pred && ds && dbias && batch > 0 && heads >= 1 && heads <= 16, "mv_heads_ds: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   dim3 grid((hw + 255) / 256, batch);
-  heads_ds_kernel<<<grid, 256, 0, stream>>>(dpred, pred, reinterpret_cast<__nv_bfloat16*>(ds), dbias, heads, hw);
+  MV_LAUNCH(heads_ds_kernel, grid, 256, 0, stream, dpred, pred, reinterpret_cast<__nv_bfloat16*>(ds), dbias, heads, hw);
   MV_CHECK_LAUNCH("heads_ds");
   return MV_OK;
 }
@@ -307,7 +313,7 @@ extern "C" int mv_heads_bwd_stencil(const void* t, const void* ds, const void* g
   MV_CHECK_ARG(t && ds && gate && dt && du && db2 && batch > 0, "mv_heads_bwd_stencil: null/empty");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long M = (long long)batch * h * w;
-  heads_bwd_stencil_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
+  MV_LAUNCH(heads_bwd_stencil_kernel, (unsigned)((M + 127) / 128), 128, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(t), reinterpret_cast<const __nv_bfloat16*>(ds),
       reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(dt),
       reinterpret_cast<__nv_bfloat16*>(du), db2, h, w, M);

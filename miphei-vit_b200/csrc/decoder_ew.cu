@@ -12,6 +12,7 @@
 namespace mv {
 
 __global__ void prep_image_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ img, int B, int S) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const long long npix = (long long)B * S * S;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -28,6 +29,7 @@ __global__ void prep_image_kernel(const float* __restrict__ x, __nv_bfloat16* __
 
 __global__ void patch_matrix_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int S, int g,
                                     int ldk) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   // one thread per (patch row, 8-wide k group); ldk = 592
   const int groups = ldk / 8;
   const long long total = (long long)B * g * g * groups;
@@ -69,6 +71,7 @@ __device__ __forceinline__ void cubic_coeffs(float t, float* w) {
 // tokens bf16 [B, ntok, ldt] (prefix tokens first) -> out NHWC bf16 [B, t, t, D]; one block per output pixel
 __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long long ldt, int ntok, int prefix, int g,
                                      int t, int D, float inv_scale, __nv_bfloat16* __restrict__ out) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int ox = blockIdx.x % t, oy = (blockIdx.x / t) % t, b = blockIdx.x / (t * t);
   const float sy = (oy + 0.5f) * inv_scale - 0.5f, sx = (ox + 0.5f) * inv_scale - 0.5f;
   const int iy = (int)floorf(sy), ix = (int)floorf(sx);
@@ -105,6 +108,7 @@ __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long
 // NHWC bf16 [B,h,w,C] -> [B,2h,2w,C], bilinear, align_corners = False; one thread per (output pixel, 8 channels)
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h,
                                   int w, int C) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
   const long long total = (long long)B * 4 * h * w * cg;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +144,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
 // prefix-token rows get zero. One block per token row.
 __global__ void tokens_to_map_bwd_kernel(const __nv_bfloat16* __restrict__ dmap, int ntok, int prefix, int g, int t, int D,
                                          float inv_scale, __nv_bfloat16* __restrict__ dtok, long long ldt) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float wy[64], wx[64];
   const int tok = blockIdx.x % ntok, b = blockIdx.x / ntok;
   __nv_bfloat16* dst = dtok + ((long long)b * ntok + tok) * ldt;
@@ -190,6 +195,7 @@ __global__ void tokens_to_map_bwd_kernel(const __nv_bfloat16* __restrict__ dmap,
 // timm _pos_embed with no_embed_class=True)
 __global__ void fill_prefix_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ prefix, int B, int ntok,
                                    int nprefix, int D) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int d4 = D / 4;
   const long long total = (long long)B * nprefix * d4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,7 +214,7 @@ extern "C" int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int ba
   MV_CHECK_ARG(x && prefix && batch > 0 && dim % 4 == 0 && ldx % 4 == 0, "mv_fill_prefix: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)batch * n_prefix * (dim / 4);
-  fill_prefix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, ldx, prefix, batch, n_tok, n_prefix, dim);
+  MV_LAUNCH(fill_prefix_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, x, ldx, prefix, batch, n_tok, n_prefix, dim);
   MV_CHECK_LAUNCH("fill_prefix");
   return MV_OK;
 }
@@ -221,14 +227,14 @@ extern "C" int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (img_nhwc8) {
     const long long npix = (long long)batch * size * size;
-    prep_image_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(img_nhwc8),
+    MV_LAUNCH(prep_image_kernel, (unsigned)((npix + 255) / 256), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(img_nhwc8),
                                                                           batch, size);
     MV_CHECK_LAUNCH("prep_image");
   }
   if (patch_matrix) {
     const int g = size / 14;
     const long long total = (long long)batch * g * g * (ldk / 8);
-    patch_matrix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+    MV_LAUNCH(patch_matrix_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
         x, reinterpret_cast<__nv_bfloat16*>(patch_matrix), batch, size, g, ldk);
     MV_CHECK_LAUNCH("patch_matrix");
   }
@@ -244,7 +250,7 @@ extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int 
   // PyTorch uses the reciprocal of the user-supplied scale factor (target/grid) for the source coordinates
   const float inv_scale = (float)(1.0 / ((double)target / (double)grid));
   const int threads = dim / 8 < 256 ? (dim / 8 + 31) / 32 * 32 : 256;
-  tokens_to_map_kernel<<<batch * target * target, threads, 0, stream>>>(
+  MV_LAUNCH(tokens_to_map_kernel, batch * target * target, threads, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
       reinterpret_cast<__nv_bfloat16*>(out));
   MV_CHECK_LAUNCH("tokens_to_map");
@@ -260,7 +266,7 @@ extern "C" int mv_tokens_to_map_bwd(const void* dmap, void* dtokens, int64_t ldt
   const float inv_scale = (float)(1.0 / ((double)target / (double)grid));
   int threads = dim / 8 < 256 ? (dim / 8 + 31) / 32 * 32 : 256;
   if (threads < 2 * target) threads = (2 * target + 31) / 32 * 32;
-  tokens_to_map_bwd_kernel<<<batch * n_tok, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dmap), n_tok, prefix,
+  MV_LAUNCH(tokens_to_map_bwd_kernel, batch * n_tok, threads, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dmap), n_tok, prefix,
                                                                  grid, target, dim, inv_scale,
                                                                  reinterpret_cast<__nv_bfloat16*>(dtokens), ldt);
   MV_CHECK_LAUNCH("tokens_to_map_bwd");
@@ -272,7 +278,7 @@ extern "C" int mv_upsample2x(const void* in, void* out, int batch, int h, int w,
   MV_CHECK_ARG(in && out && batch > 0 && h > 0 && w > 0 && c % 8 == 0, "mv_upsample2x: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)batch * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  MV_LAUNCH(upsample2x_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
   MV_CHECK_LAUNCH("upsample2x");
   return MV_OK;

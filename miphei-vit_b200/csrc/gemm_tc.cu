@@ -74,7 +74,16 @@ struct GemmCfg {
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid through one MUFU op: sigma(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx: ~2^-11 relative error, far below the
+// bf16 rounding of everything these epilogues store); the exp + full-precision divide form costs ~12 instructions and two
+// MUFU ops per element, which made the SwiGLU epilogues issue-bound
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 
 // ------------------------------------------------------------------ epilogue pieces (one thread = one output row)
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* f) {
@@ -195,6 +204,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_sync();  // PDL: the prologue above overlapped the previous kernel's tail; its results are visible from here on
 
   const int num_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = num_mn * p.splits;
@@ -405,6 +415,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           load_resid(0, qn);
         }
       }
+      // SWIGLU_BWD: the saved pre-activations [g | v] of a 32-column chunk (4 row groups per lane), fetched one chunk
+      // ahead — the first one before waiting for the accumulator — so their DRAM latency hides behind the MMAs
+      uint4 hgn[4], hvn[4];
+      auto load_h = [&](int c, uint4* hg, uint4* hv) {
+        const int jj = n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 8 + (lane >> 2);
+          hg[it] = make_uint4(0, 0, 0, 0);
+          hv[it] = hg[it];
+          if (mm < p.m && jj < p.n) {
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)mm * p.ldin2;
+            hg[it] = *reinterpret_cast<const uint4*>(h + jj);
+            hv[it] = *reinterpret_cast<const uint4*>(h + p.n + jj);
+          }
+        }
+      };
+      if constexpr (MODE == MV_GEMM_SWIGLU_BWD) load_h(egrp, hgn, hvn);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
@@ -732,19 +760,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
           const int col = (lane & 3) * 8;
           const int jj = n_blk * BLOCK_N + c * 32 + col;
-          // the saved pre-activations are fetched for all 4 row groups before any store (loads stay in flight together)
           uint4 hg[4], hv[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int mm = m_warp + it * 8 + (lane >> 2);
-            hg[it] = make_uint4(0, 0, 0, 0);
-            hv[it] = hg[it];
-            if (mm < p.m && jj < H) {
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)mm * p.ldin2;
-              hg[it] = *reinterpret_cast<const uint4*>(h + jj);
-              hv[it] = *reinterpret_cast<const uint4*>(h + H + jj);
-            }
-          }
+          for (int it = 0; it < 4; ++it) { hg[it] = hgn[it]; hv[it] = hvn[it]; }
+          if (c + EGRPS < BLOCK_N / 32) load_h(c + EGRPS, hgn, hvn);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + (lane >> 2);
@@ -759,7 +778,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 fg = unpack_bf16x2(pg[j]), fv = unpack_bf16x2(pv[j]);
-                const float s0 = 1.f / (1.f + __expf(-fg.x)), s1 = 1.f / (1.f + __expf(-fg.y));
+                const float s0 = sigmoid_f(fg.x), s1 = sigmoid_f(fg.y);
                 dg[2 * j] = du[2 * j] * fv.x * (s0 * (1.f + fg.x * (1.f - s0)));
                 dg[2 * j + 1] = du[2 * j + 1] * fv.y * (s1 * (1.f + fg.y * (1.f - s1)));
                 dv[2 * j] = du[2 * j] * fg.x * s0;
@@ -868,29 +887,13 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   if (PAIR) {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(gemm_threads(MODE));
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *ta2, *tb, p);
-    if (e != cudaSuccess) {
-      set_error("gemm_bf16_tc (cta pair) launch failed: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
+    (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, p);
     MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
     return MV_OK;
   }
   if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
   if (tiles < grid) grid = tiles;
-  kern<<<grid, gemm_threads(MODE), Cfg::kSmemBytes, stream>>>(*ta, *ta2, *tb, p);
+  MV_LAUNCH(kern, grid, gemm_threads(MODE), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
 }
@@ -944,11 +947,17 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   switch (a.mode) {
     case MV_GEMM_SWIGLU:
       MV_CHECK_ARG(a.n % 256 == 0 && a.shift && !a.out_f32, "mv_gemm_bf16(SWIGLU): N %% 256 == 0, bias required, bf16 out");
-      // measured: the epilogue-heavy SwiGLU tile is no faster as a CTA pair (the MMA waits for both CTAs' epilogues)
-      if (pair_legal && a.reserved2 == 2) return launch_gemm<256, MV_GEMM_SWIGLU, true>(a, stream);
+      // with 8 epilogue warps the CTA pair wins (M=5264: 112 -> 100 us, 1320 TFLOP/s); reserved2 == 1 forces single CTAs
+      if (pair_legal && (a.reserved2 == 2 || (a.reserved2 == 0 && a.m >= 1024))) return launch_gemm<256, MV_GEMM_SWIGLU, true>(a, stream);
       return launch_gemm<256, MV_GEMM_SWIGLU>(a, stream);
     case MV_GEMM_SWIGLU_BWD:
       MV_CHECK_ARG(a.in2 && a.ldin2 % 8 == 0 && !a.out_f32, "mv_gemm_bf16(SWIGLU_BWD): in2 required, bf16 out");
+      // 256 hidden units per tile on a CTA pair by default (M=10528: 131 us vs 168 us for 128-wide single-CTA tiles)
+      if (a.n % 256 == 0 && (a.block_n == 256 || (a.block_n == 0 && a.m >= 1024))) {
+        if (pair_legal && (a.reserved2 == 2 || (a.reserved2 == 0 && a.m >= 1024)))
+          return launch_gemm<256, MV_GEMM_SWIGLU_BWD, true>(a, stream);
+        return launch_gemm<256, MV_GEMM_SWIGLU_BWD>(a, stream);
+      }
       if (pair_legal && a.reserved2 == 2) return launch_gemm<128, MV_GEMM_SWIGLU_BWD, true>(a, stream);
       return launch_gemm<128, MV_GEMM_SWIGLU_BWD>(a, stream);
     case MV_GEMM_NN_ATOMIC:

@@ -30,6 +30,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a
 // gram: fp32 [40, 32], pre-zeroed; rows 0..31 += f^T f, row 32 += 1^T f  (the layout the heads backward consumes)
 __global__ void __launch_bounds__(GRAM_THREADS) gram32_kernel(const __nv_bfloat16* __restrict__ f, long long ldf, long long M,
                                                               float* __restrict__ gram) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ __align__(16) __nv_bfloat16 stage[GRAM_THREADS / 32][GRAM_CHUNK * GRAM_PITCH];
   __shared__ float red[33 * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,6 +131,7 @@ __global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double
                                           float* __restrict__ running_var, float momentum, float eps, int C,
                                           float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                           float* __restrict__ rstd_out) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ double cov[32 * 32];
   __shared__ double mf[32];
   if (threadIdx.x < 32) mf[threadIdx.x] = (double)gram[32 * 32 + threadIdx.x] / count;
@@ -176,7 +178,7 @@ extern "C" int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, voi
   const int sms = device_sms() > 0 ? device_sms() : 148;
   long long grid = (nchunks + (GRAM_THREADS / 32) - 1) / (GRAM_THREADS / 32);
   if (grid > 4ll * sms) grid = 4ll * sms;
-  gram32_kernel<<<(unsigned)grid, GRAM_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
+  MV_LAUNCH(gram32_kernel, (unsigned)grid, GRAM_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
   MV_CHECK_LAUNCH("gram32");
   return MV_OK;
 }
@@ -189,7 +191,7 @@ extern "C" int mv_heads_bn_from_gram(const float* gram, double count, const floa
                "mv_heads_bn_from_gram: null/empty");
   MV_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "mv_heads_bn_from_gram: running stats go together");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  heads_bn_from_gram_kernel<<<(c + 63) / 64, 64, 0, stream>>>(gram, count, w1, b1, gamma, beta, running_mean, running_var,
+  MV_LAUNCH(heads_bn_from_gram_kernel, (c + 63) / 64, 64, 0, stream, gram, count, w1, b1, gamma, beta, running_mean, running_var,
                                                              momentum, eps, c, scale, shift, mean, rstd);
   MV_CHECK_LAUNCH("heads_bn_from_gram");
   return MV_OK;

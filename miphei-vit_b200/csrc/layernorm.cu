@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
                                                                       __nv_bfloat16* __restrict__ y, long long ldy,
                                                                       float* __restrict__ mean_out,
                                                                       float* __restrict__ rstd_out, int M, float eps) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
                                                                       float* __restrict__ dx, long long lddx,
                                                                       __nv_bfloat16* __restrict__ dx_bf16,
                                                                       long long lddxb, int M, float eps) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -148,7 +150,7 @@ extern "C" int mv_layernorm_fwd(const float* x, int64_t ldx, const float* w, con
   MV_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mv_layernorm_fwd: mean and rstd go together");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = (m + LN_WARPS - 1) / LN_WARPS;
-  MV_LN_DISPATCH(d / 128, (layernorm_fwd_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(
+  MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_fwd_kernel<V>), grid, LN_WARPS * 32, 0, stream, 
                               x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, m, eps)));
   MV_CHECK_LAUNCH("layernorm_fwd");
   return MV_OK;
@@ -165,10 +167,10 @@ extern "C" int mv_layernorm_bwd(const float* x, int64_t ldx, const float* w, con
   const int grid = (m + LN_WARPS - 1) / LN_WARPS;
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   if (dy_f32) {
-    MV_LN_DISPATCH(d / 128, (layernorm_bwd_kernel<V, true><<<grid, LN_WARPS * 32, 0, stream>>>(
+    MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_bwd_kernel<V, true>), grid, LN_WARPS * 32, 0, stream, 
                                 x, ldx, w, dy, lddy, dres, lddres, dx, lddx, dxb, lddxb, m, eps)));
   } else {
-    MV_LN_DISPATCH(d / 128, (layernorm_bwd_kernel<V, false><<<grid, LN_WARPS * 32, 0, stream>>>(
+    MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_bwd_kernel<V, false>), grid, LN_WARPS * 32, 0, stream, 
                                 x, ldx, w, dy, lddy, dres, lddres, dx, lddx, dxb, lddxb, m, eps)));
   }
   MV_CHECK_LAUNCH("layernorm_bwd");

@@ -17,6 +17,7 @@ namespace mv {
 __global__ void transpose16_kernel(const __nv_bfloat16* __restrict__ src0, long long ld0,
                                    const __nv_bfloat16* __restrict__ src1, long long ld1, __nv_bfloat16* __restrict__ dst0,
                                    __nv_bfloat16* __restrict__ dst1, long long ldt, int M) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const __nv_bfloat16* s = blockIdx.y == 0 ? src0 : src1;
@@ -37,6 +38,7 @@ __global__ void transpose16_kernel(const __nv_bfloat16* __restrict__ src0, long 
 __global__ void lora_unpack_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, float* __restrict__ dAq,
                                    float* __restrict__ dAv, float* __restrict__ dBq, float* __restrict__ dBv, int D,
                                    float alpha) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 8*D
   if (i >= 8 * D) return;
   const int r = i / D, d = i - r * D;
@@ -72,7 +74,7 @@ extern "C" int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_e
   const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(xn_ext);
   const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(dqkv_ext);
   dim3 grid((m + 255) / 256, 2);
-  transpose16_kernel<<<grid, 256, 0, stream>>>(xe + d, ldx, qe + 3ll * d, ldq, tT, dtT, ldt, m);
+  MV_LAUNCH(transpose16_kernel, grid, 256, 0, stream, xe + d, ldx, qe + 3ll * d, ldq, tT, dtT, ldt, m);
   MV_CHECK_LAUNCH("transpose16");
   cudaError_t e = cudaMemsetAsync(g_a, 0, (16ll * d + 16ll * 3 * d) * 4, stream);
   if (e != cudaSuccess) {
@@ -93,7 +95,7 @@ extern "C" int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_e
   a.a = tT; a.b = dqkv_ext; a.ldb = ldq; a.n = 3 * d; a.out = g_b; a.ldo = 3 * d;
   rc = mv_gemm_bf16(&a, stream_);
   if (rc) return rc;
-  lora_unpack_kernel<<<(8 * d + 255) / 256, 256, 0, stream>>>(g_a, g_b, dA_q, dA_v, dB_q, dB_v, d, alpha);
+  MV_LAUNCH(lora_unpack_kernel, (8 * d + 255) / 256, 256, 0, stream, g_a, g_b, dA_q, dA_v, dB_q, dB_v, d, alpha);
   MV_CHECK_LAUNCH("lora_unpack");
   return MV_OK;
 }

@@ -1,6 +1,7 @@
 // Host plumbing: init, error strings, launch counter, TMA descriptor creation through the driver entry point
 // (resolved at run time with cudaGetDriverEntryPoint so the library does not link libcuda).
 #include "mv_host.h"
+#include <stdlib.h>
 
 #include <stdarg.h>
 #include <string.h>
@@ -28,6 +29,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int device_sms() { return g_sms; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MV_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* ptr, const uint64_t* dims,

@@ -26,6 +26,39 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* p
                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
                 const uint32_t* elem_strides = nullptr);
 
+// Launch with programmatic stream serialization (PDL) — the kernel MUST call griddep_wait() (mv_ptx.cuh) before touching
+// global memory. MV_PDL=0 in the environment turns the attribute off (plain stream order). cluster_x > 1 adds a cluster.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// MV_LAUNCH(kernel, grid, block, smem, stream, args...): PDL launch, errors surface through MV_CHECK_LAUNCH
+#define MV_LAUNCH(kern, grid, block, smem, stream, ...) \
+  (void)mv::launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), stream, 1, __VA_ARGS__)
+
 #define MV_CHECK_ARG(cond, ...)       \
   do {                                \
     if (!(cond)) {                    \

@@ -27,6 +27,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library is launched with programmatic stream serialization (mv_host.h: launch_pdl): its CTAs may
+// become resident while the previous kernel of the stream is still draining, run their prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and then block in griddep_wait() until the previous grid has completed and its
+// memory is visible.  EVERY thread calls griddep_wait() before its first global-memory access (reads AND writes), which
+// also makes the ordering transitive along the stream.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_sync() {
+  griddep_wait();
+  griddep_launch();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_fwd_bwd_kernel(const float*
                                                                     int B, int mode, float lambda, float grad_scale,
                                                                     float* __restrict__ partial_sq,
                                                                     float* __restrict__ partial_abs) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float sh[8];
   const int plane = blockIdx.y;  // b * C + c
   const int c = plane % C;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_fwd_bwd_kernel(const float*
 __global__ void loss_finalize_kernel(const float* __restrict__ partial_sq, const float* __restrict__ partial_abs,
                                      const float* __restrict__ weights, int C, int B, int HW, int nblk, int mode,
                                      float lambda, float* __restrict__ loss) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ double shd[256];
   double acc = 0.0;
   const int total = B * C * nblk;
@@ -95,6 +97,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial_sq, const
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n,
                                                             float* __restrict__ partial) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float sh[8];
   float s = 0.f;
   const long long n4 = n / 4;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 
 // norm_out[0] = sqrt(sum of partials) (fixed order, double accumulation), norm_out[1] = clip coefficient
 __global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, float max_norm, float* __restrict__ norm_out) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ double shd[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         const float* __restrict__ norm_coef, float grad_mul, float lr,
                                                         float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const float coef = (norm_coef ? norm_coef[1] : 1.f) * grad_mul;
   const float step = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -160,10 +165,10 @@ extern "C" int mv_loss_fwd_bwd(const float* pred, const float* target, float* gr
   float* psq = workspace;
   float* pab = workspace + (long long)batch * chans * nblk;
   dim3 grid(nblk, batch * chans);
-  loss_fwd_bwd_kernel<<<grid, LOSS_THREADS, 0, stream>>>(pred, target, grad, weights, chans, hw, batch, mode, lambda,
+  MV_LAUNCH(loss_fwd_bwd_kernel, grid, LOSS_THREADS, 0, stream, pred, target, grad, weights, chans, hw, batch, mode, lambda,
                                                          grad_scale, psq, pab);
   MV_CHECK_LAUNCH("loss_fwd_bwd");
-  loss_finalize_kernel<<<1, 256, 0, stream>>>(psq, pab, weights, chans, batch, hw, nblk, mode, lambda, loss);
+  MV_LAUNCH(loss_finalize_kernel, 1, 256, 0, stream, psq, pab, weights, chans, batch, hw, nblk, mode, lambda, loss);
   MV_CHECK_LAUNCH("loss_finalize");
   return MV_OK;
 }
@@ -184,9 +189,9 @@ extern "C" int mv_grad_norm(const float* grads, int64_t n, float max_norm, float
   int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > 1024) blocks = 1024;
   if (blocks < 1) blocks = 1;
-  sumsq_partial_kernel<<<blocks, 256, 0, stream>>>(grads, n, workspace);
+  MV_LAUNCH(sumsq_partial_kernel, blocks, 256, 0, stream, grads, n, workspace);
   MV_CHECK_LAUNCH("sumsq_partial");
-  norm_finalize_kernel<<<1, 256, 0, stream>>>(workspace, blocks, max_norm, norm_out);
+  MV_LAUNCH(norm_finalize_kernel, 1, 256, 0, stream, workspace, blocks, max_norm, norm_out);
   MV_CHECK_LAUNCH("norm_finalize");
   return MV_OK;
 }
@@ -203,7 +208,7 @@ extern "C" int mv_adam_clip_step(float* params, const float* grads, float* exp_a
   int blocks = (int)((n + 255) / 256);
   const int cap = (device_sms() > 0 ? device_sms() : 148) * 8;
   if (blocks > cap) blocks = cap;
-  adam_clip_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, norm_coef, grad_mul, lr, beta1, beta2,
+  MV_LAUNCH(adam_clip_kernel, blocks, 256, 0, stream, params, grads, exp_avg, exp_avg_sq, n, norm_coef, grad_mul, lr, beta1, beta2,
                                                eps, (float)bc1, (float)sqrt(bc2));
   MV_CHECK_LAUNCH("adam_clip");
   return MV_OK;
