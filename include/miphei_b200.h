@@ -113,6 +113,11 @@ typedef struct mv_gemm_args {
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
+/* Diagnostics: when buf != NULL every following mv_gemm_bf16 launch writes 16 int64 per CTA into buf[16 * blockIdx.x ..]:
+ * cycles [0] producer waiting for smem, [1] MMA waiting for operands, [2] MMA waiting for an accumulator, [3] epilogue
+ * waiting for an accumulator, [4] epilogue busy, [5] producer lifetime, [6] tiles; %globaltimer ns at [8] kernel entry,
+ * [9] after the prologue / grid-dependency wait, [10] CTA end.  buf must hold 16 * 2 * num_sms int64. NULL disables. */
+void mv_gemm_set_profile_buffer(void* buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm over channels of token rows (timm Block.norm1/norm2, final norm; eps 1e-6).

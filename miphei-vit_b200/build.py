@@ -26,9 +26,13 @@ def _newest_header():
     return t
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, prof=False):
+    """prof=True builds the diagnostic twin libmiphei_b200_prof.so (-DMV_GEMM_PROFILE=1: per-role cycle counters in the
+    GEMM kernel, tools/gemm_roles.py); the production library carries no instrumentation."""
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
-    bdir = os.path.join(CSRC, "build")
+    bdir = os.path.join(CSRC, "build_prof" if prof else "build")
+    flags = FLAGS + (["-DMV_GEMM_PROFILE=1"] if prof else [])
+    out = OUT.replace(".so", "_prof.so") if prof else OUT
     os.makedirs(bdir, exist_ok=True)
     hdr_t = _newest_header()
     jobs = []
@@ -42,7 +46,7 @@ def build(verbose=False, force=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + flags + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
@@ -57,13 +61,13 @@ def build(verbose=False, force=False):
                 if verbose:
                     print("== " + os.path.basename(src))
                     print(log)
-    if jobs or not os.path.exists(OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if jobs or not os.path.exists(out):
+        cmd = [NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, prof="--prof" in sys.argv))

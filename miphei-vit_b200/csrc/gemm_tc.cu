@@ -19,8 +19,22 @@ constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
 // the SwiGLU epilogues (exp per element, extra loads / stores) need twice the epilogue warps to keep up with the MMAs:
 // two warps per TMEM lane quadrant, each taking every other 32-column chunk
-__host__ __device__ constexpr int gemm_epi_warps(int mode) { return (mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD) ? 8 : 4; }
-__host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * gemm_epi_warps(mode); }
+// Role-stall counters (mv_gemm_set_profile_buffer) are compiled in only with -DMV_GEMM_PROFILE=1 (the diagnostic library
+// libmiphei_b200_prof.so built by `python miphei-vit_b200/build.py --prof`); the production kernels carry none of it.
+#ifndef MV_GEMM_PROFILE
+#define MV_GEMM_PROFILE 0
+#endif
+constexpr bool kProf = MV_GEMM_PROFILE != 0;
+#ifndef MV_LINEAR_EPI_WARPS
+#define MV_LINEAR_EPI_WARPS 4  // 8 spills on the fp32 + residual path (204-register cap) and loses 30-50 % there
+#endif
+__host__ __device__ constexpr int gemm_epi_warps(int mode, int block_n, bool light) {
+  return (mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD) ? 8
+         : (mode == MV_GEMM_LINEAR && block_n >= 128 && !light) ? MV_LINEAR_EPI_WARPS : 4;
+}
+__host__ __device__ constexpr int gemm_threads(int mode, int block_n, bool light) {
+  return 64 + 32 * gemm_epi_warps(mode, block_n, light);
+}
 
 struct GemmDev {
   int m, n, k;
@@ -45,6 +59,11 @@ struct GemmDev {
   int conv_tw;         // tile = conv_tw x (128 / conv_tw) output pixels (full rows when conv_w < 128)
   int conv_stride;     // 1 or 2
   int conv_cb0, conv_cb1;  // 64-channel blocks per tap taken from source 0 / source 1 (channel concat)
+  // diagnostics (mv_gemm_set_profile_buffer): per CTA 8 x int64 cycle counters, nullptr in production
+  //   [0] producer waiting for a free smem slot   [1] MMA warp waiting for operands   [2] MMA warp waiting for a free
+  //   accumulator   [3] epilogue warp 2 waiting for an accumulator   [4] epilogue warp 2 busy   [5] CTA lifetime
+  //   [6] tiles of this CTA
+  long long* prof;
 };
 
 // PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
@@ -58,8 +77,13 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiWarps = gemm_epi_warps(MODE);
-  static constexpr int kRingBudget = (kEpiWarps == 8 ? 177 : 196) * 1024;  // leave room for the larger staging area
+  static constexpr int kEpiWarps = gemm_epi_warps(MODE, BLOCK_N, LIGHT);
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
+  static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
+  // LINEAR: per-epilogue-warp copy of the tile's (scale, shift) columns, staged before the accumulator is awaited
+  static constexpr int kCoefBytes = (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) ? kEpiWarps * 2 * BLOCK_N * 4 : 0;
+  static constexpr int kFixedBytes = 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes + kCoefBytes;
+  static constexpr int kRingBudget = 227 * 1024 - kFixedBytes;
   static constexpr int kStagesDeep = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kStages = !LIGHT ? kStagesDeep : (BLOCK_N <= 32 ? 4 : BLOCK_N <= 64 ? 3 : 2);
   // HEAD_CONV keeps the 9 taps in separate 16-column accumulators (144 columns per stage, stage stride 256)
@@ -67,9 +91,8 @@ struct GemmCfg {
   static constexpr int kTmemRaw = 2 * BLOCK_N;
   static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512
                                    : kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
-  static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -152,11 +175,13 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 
 // ------------------------------------------------------------------ kernel
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
-__global__ void __launch_bounds__(gemm_threads(MODE), LIGHT ? 2 : 1)
+__global__ void __launch_bounds__(gemm_threads(MODE, BLOCK_N, LIGHT), LIGHT ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
   constexpr int STAGES = Cfg::kStages;
+  unsigned long long prof_ns0 = 0;
+  if (kProf && p.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
   static_assert(!LIGHT || (2 * Cfg::kTmemCols <= 512 && !PAIR), "two resident CTAs must share the 512 TMEM columns");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -177,7 +202,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* staging_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::kStageBytes + 256);
-  float* cstat = staging_all + Cfg::kEpiWarps * 32 * 36;  // [2][BLOCK_N]
+  float* cstat = staging_all + Cfg::kEpiWarps * 32 * 36;  // [2][256]
+  float* coef_all = cstat + 2 * 256;                      // [epilogue warp][scale BLOCK_N | shift BLOCK_N]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -205,6 +231,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_sync();  // PDL: the prologue above overlapped the previous kernel's tail; its results are visible from here on
+  long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long prof_t0 = (kProf && p.prof) ? clock64() : 0;
+  if (kProf && p.prof && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.prof[16ll * blockIdx.x + 8] = (long long)prof_ns0;
+    p.prof[16ll * blockIdx.x + 9] = (long long)t;
+  }
 
   const int num_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = num_mn * p.splits;
@@ -240,7 +274,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         const int cbt = p.conv_cb0 + p.conv_cb1;
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long t0_ = (kProf && p.prof) ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1);
+          if (kProf && p.prof) prof_acc[0] += clock64() - t0_;
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const bool nn_conv = MODE == MV_GEMM_NN_ATOMIC && p.conv;
@@ -315,11 +351,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int split = tile / num_mn;
         const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
+        long long t0_ = (kProf && p.prof) ? clock64() : 0;
         mbar_wait(tempty_bar(as), aphase ^ 1);
+        if (kProf && p.prof) prof_acc[2] += clock64() - t0_;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
+          t0_ = (kProf && p.prof) ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
+          if (kProf && p.prof) prof_acc[1] += clock64() - t0_;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -361,19 +401,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     int stat_nblk = -1;
+    constexpr int EPT = 32 * Cfg::kEpiWarps;  // epilogue threads
+    auto ep_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory"); };
     auto flush_stats = [&](int nb) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) {
+      ep_bar();
+      for (int i = ep_tid; i < 2 * BLOCK_N; i += EPT) {
         const float v = cstat[i];
         const int col = nb * BLOCK_N + (i % BLOCK_N);
         if (v != 0.f && col < p.n) atomicAdd(p.colstats + (i / BLOCK_N) * p.n + col, v);
         cstat[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      ep_bar();
     };
     if (MODE == MV_GEMM_LINEAR && p.colstats) {
-      for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) cstat[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = ep_tid; i < 2 * BLOCK_N; i += EPT) cstat[i] = 0.f;
+      ep_bar();
     }
     for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
       const int mn = tile % num_mn;
@@ -385,9 +427,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       const int m = m_blk * GEMM_BLOCK_M + row_in_tile;
       const bool row_ok = m < p.m;
-      // fp32-output path: output / residual row of each of this lane's 8 row slots, and the residual of the first column
-      // chunk fetched BEFORE waiting for the accumulator (the load latency hides behind the MMAs of this tile)
-      long long orow_[8], rrow_[8];
+      // row remap of the patch-embedding GEMM (patch rows -> token rows); identity for everything else
+      auto map_rows = [&](int mm, long long& orow, long long& rrow) {
+        orow = mm;
+        rrow = mm;
+        if (p.rows_per_group > 0) {
+          const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
+          orow = (long long)g * p.group_stride + rr + p.row_offset;
+          rrow = p.resid_row_mod ? rr : orow;
+        }
+      };
+      // fp32-output path: the residual of a 32-column chunk (8 row slots per lane) is fetched one chunk ahead, the first
+      // one BEFORE waiting for the accumulator (the load latency hides behind the MMAs of this tile)
       float4 qn[8];
       auto load_resid = [&](int c, float4* q) {
         const int nn = n_blk * BLOCK_N + c * 32 + (lane & 7) * 4;
@@ -395,25 +446,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int it = 0; it < 8; ++it) {
           const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 4 + (lane >> 3);
           q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.resid && mm < p.m && nn < p.n) q[it] = *reinterpret_cast<const float4*>(p.resid + rrow_[it] * p.ldr + nn);
+          if (p.resid && mm < p.m && nn < p.n) {
+            long long orow, rrow;
+            map_rows(mm, orow, rrow);
+            q[it] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + nn);
+          }
         }
       };
+      float* coef = coef_all + ew * (2 * BLOCK_N);
       if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
-        if (p.out_f32) {
+        // this tile's (scale, shift) columns -> warp-private smem, also ahead of the accumulator wait
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 4 + (lane >> 3);
-            long long orow = mm, rrow = mm;
-            if (p.rows_per_group > 0) {
-              const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
-              orow = (long long)g * p.group_stride + rr + p.row_offset;
-              rrow = p.resid_row_mod ? rr : orow;
-            }
-            orow_[it] = orow;
-            rrow_[it] = rrow;
+        for (int i = lane * 4; i < BLOCK_N; i += 128) {
+          const int nn = n_blk * BLOCK_N + i;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nn < p.n) {
+            if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
+            if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
           }
-          load_resid(0, qn);
+          *reinterpret_cast<float4*>(coef + i) = sc;
+          *reinterpret_cast<float4*>(coef + BLOCK_N + i) = sh;
         }
+        if (p.out_f32) load_resid(egrp, qn);
+        __syncwarp();
       }
       // SWIGLU_BWD: the saved pre-activations [g | v] of a 32-column chunk (4 row groups per lane), fetched one chunk
       // ahead — the first one before waiting for the accumulator — so their DRAM latency hides behind the MMAs
@@ -433,29 +488,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       if constexpr (MODE == MV_GEMM_SWIGLU_BWD) load_h(egrp, hgn, hvn);
+      const long long te0_ = (kProf && p.prof) ? clock64() : 0;
       mbar_wait(tfull_bar(as), aphase);
+      const long long te1_ = (kProf && p.prof) ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
 
       if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
         // TMEM (one row per lane) -> padded smem tile -> row-contiguous global accesses (coalesced residual read,
         // output write); scale / shift are per column, so they are applied after the transpose (fixed per lane).
-        float* stg = staging_all + quad * (32 * 36);
+        // The TMEM load of chunk c+1 is issued as soon as chunk c sits in smem, so it overlaps the store phase.
+        float* stg = staging_all + ew * (32 * 36);
         const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
+        constexpr int NC = BLOCK_N / 32;
+        uint32_t v[32];
+        tmem_ld32(taddr + egrp * 32, v);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          float4 q_[8];
-          if (p.out_f32) {  // residual of this chunk was prefetched; start fetching the next chunk's now
-#pragma unroll
-            for (int it = 0; it < 8; ++it) q_[it] = qn[it];
-            if (c + 1 < BLOCK_N / 32) load_resid(c + 1, qn);
-          }
+        for (int c = egrp; c < NC; c += EGRPS) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (c + EGRPS < NC) tmem_ld32(taddr + (c + EGRPS) * 32, v);
+          float4 q_[8];
+          if (p.out_f32) {  // residual of this chunk was prefetched; start fetching the next chunk's now
+#pragma unroll
+            for (int it = 0; it < 8; ++it) q_[it] = qn[it];
+            if (c + EGRPS < NC) load_resid(c + EGRPS, qn);
+          }
           __syncwarp();
           const int n0 = n_blk * BLOCK_N + c * 32;
           if (p.out_f32) {
@@ -463,9 +523,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int nn = n0 + col;
             float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f), cq4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (nn < p.n) {
-              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nn));
-              if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
+              const float4 sc = *reinterpret_cast<const float4*>(coef + c * 32 + col);
+              const float4 sh = *reinterpret_cast<const float4*>(coef + BLOCK_N + c * 32 + col);
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const int r = it * 4 + (lane >> 3);
@@ -477,7 +536,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   a.x += q_[it].x; a.y += q_[it].y; a.z += q_[it].z; a.w += q_[it].w;
                   cs4.x += a.x; cs4.y += a.y; cs4.z += a.z; cs4.w += a.w;
                   cq4.x += a.x * a.x; cq4.y += a.y * a.y; cq4.z += a.z * a.z; cq4.w += a.w * a.w;
-                  const long long orow = orow_[it];
+                  long long orow, rrow;
+                  map_rows(mm, orow, rrow);
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nn) = a;
                   if (p.aux) {
                     uint2 u;
@@ -508,16 +568,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int nn = n0 + col;
             const bool col_ok = nn < p.n;
             float sc[8], sh[8], csum[8], csq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; csum[j] = 0.f; csq[j] = 0.f; }
-            if (p.scale && col_ok) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + nn + 4));
+            {
+              const float4 s0 = *reinterpret_cast<const float4*>(coef + c * 32 + col);
+              const float4 s1 = *reinterpret_cast<const float4*>(coef + c * 32 + col + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(coef + BLOCK_N + c * 32 + col);
+              const float4 h1 = *reinterpret_cast<const float4*>(coef + BLOCK_N + c * 32 + col + 4);
               sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
             }
-            if (p.shift && col_ok) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + nn)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + nn + 4));
-              sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = it * 8 + (lane >> 2);
@@ -536,12 +596,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? du : 0.f;
                 }
-                long long orow = mm, rrow = mm;
-                if (p.rows_per_group > 0) {
-                  const int g = mm / p.rows_per_group, rr = mm - g * p.rows_per_group;
-                  orow = (long long)g * p.group_stride + rr + p.row_offset;
-                  rrow = p.resid_row_mod ? rr : orow;
-                }
+                long long orow, rrow;
+                map_rows(mm, orow, rrow);
                 if (p.resid) {
                   const float* q = p.resid + rrow * p.ldr + nn;
                   const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
@@ -797,18 +853,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) {
         if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
       }
+      if (kProf && p.prof && warp == 2) {
+        prof_acc[3] += te1_ - te0_;
+        prof_acc[4] += clock64() - te1_;
+        prof_acc[6] += 1;
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (MODE == MV_GEMM_LINEAR && p.colstats && stat_nblk >= 0) flush_stats(stat_nblk);
   }
 
+  if (kProf && p.prof && lane == 0 && warp <= 2) {
+    long long* q = p.prof + 16ll * blockIdx.x;
+    if (warp == 0) { q[0] = prof_acc[0]; q[5] = clock64() - prof_t0; }
+    if (warp == 1) { q[1] = prof_acc[1]; q[2] = prof_acc[2]; }
+    if (warp == 2) { q[3] = prof_acc[3]; q[4] = prof_acc[4]; q[6] = prof_acc[6]; }
+  }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (kProf && p.prof && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.prof[16ll * blockIdx.x + 10] = (long long)t;
+  }
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
+
+static long long* g_gemm_prof = nullptr;  // diagnostics only (mv_gemm_set_profile_buffer)
 
 // ------------------------------------------------------------------ host launch
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
@@ -867,6 +941,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.resid_row_mod = a.resid_row_mod;
   p.splits = 1;
   p.colstats = a.colstats;
+  p.prof = g_gemm_prof;
   if (MODE == MV_GEMM_NN_ATOMIC) {
     const int sms = device_sms() > 0 ? device_sms() : 148;
     const int mn = p.num_m_blocks * p.num_n_blocks;
@@ -887,18 +962,20 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   if (PAIR) {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
-    (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, p);
+    (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE, BLOCK_N, LIGHT)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, p);
     MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
     return MV_OK;
   }
   if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
   if (tiles < grid) grid = tiles;
-  MV_LAUNCH(kern, grid, gemm_threads(MODE), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, p);
+  MV_LAUNCH(kern, grid, gemm_threads(MODE, BLOCK_N, LIGHT), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
 }
 
 }  // namespace mv
+
+extern "C" void mv_gemm_set_profile_buffer(void* buf) { mv::g_gemm_prof = reinterpret_cast<long long*>(buf); }
 
 extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   using namespace mv;

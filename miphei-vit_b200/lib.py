@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmiphei_b200.so")
+# MIPHEI_B200_LIB selects another build of the SAME library (the diagnostic twin libmiphei_b200_prof.so) — never a fallback
+LIB_PATH = os.environ.get("MIPHEI_B200_LIB") or os.path.join(_HERE, "libmiphei_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -48,6 +49,7 @@ _SIGNATURES = {
     "mv_launch_count": (c_i64, []),
     "mv_reset_launch_count": (None, []),
     "mv_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "mv_gemm_set_profile_buffer": (None, [c_void_p]),
     "mv_layernorm_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int,
                                  c_int, c_float, c_void_p]),
     "mv_layernorm_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
