@@ -58,6 +58,7 @@ struct GemmDev {
   int conv_h, conv_w;  // OUTPUT spatial size
   int conv_tw;         // tile = conv_tw x (128 / conv_tw) output pixels (full rows when conv_w < 128)
   int conv_stride;     // 1 or 2
+  int conv_rows_per_kb;  // wgrad: map rows covered by one 64-pixel k block when conv_w < 64
   int conv_cb0, conv_cb1;  // 64-channel blocks per tap taken from source 0 / source 1 (channel concat)
   // diagnostics (mv_gemm_set_profile_buffer): per CTA 8 x int64 cycle counters, nullptr in production
   //   [0] producer waiting for a free smem slot   [1] MMA warp waiting for operands   [2] MMA warp waiting for a free
@@ -273,6 +274,40 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           cv_x = rem - cv_y * p.conv_w;
         }
         const int cbt = p.conv_cb0 + p.conv_cb1;
+        // the single producer thread is on the critical path of small-tile convolutions: no integer divisions inside
+        // the k loop — tap / channel-block indices and the wgrad pixel coordinates advance incrementally
+        int f_cbi = 0, f_kx = 0, f_ky = 0;  // forward / dgrad implicit GEMM: k block -> (tap, 64-channel block)
+        if (p.conv && MODE != MV_GEMM_NN_ATOMIC && kb0 != 0) {
+          const int tap = kb0 / cbt;
+          f_cbi = kb0 - tap * cbt;
+          f_ky = tap / 3;
+          f_kx = tap - f_ky * 3;
+        }
+        // weight gradient: per tile the (tap, channel block) of each 64-column slice of B is fixed; per k block only the
+        // 64-pixel window moves
+        constexpr int NSL = BLOCK_N / 64 > 0 ? BLOCK_N / 64 : 1;
+        int w_ok[NSL], w_c[NSL], w_dx[NSL], w_dy[NSL], w_src[NSL];
+        int w_nvalid = 0, w_pb = 0, w_py = 0, w_px = 0;
+        if (MODE == MV_GEMM_NN_ATOMIC && p.conv) {
+#pragma unroll
+          for (int ns = 0; ns < NSL; ++ns) {
+            const int nb = n_blk * NSL + ns;
+            w_ok[ns] = nb < 9 * cbt;
+            const int tap = nb / cbt, cbi = nb - tap * cbt;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            w_src[ns] = cbi < p.conv_cb0 ? 0 : 1;
+            w_c[ns] = (cbi < p.conv_cb0 ? cbi : cbi - p.conv_cb0) * 64;
+            w_dx[ns] = kx - 1;
+            w_dy[ns] = ky - 1;
+            w_nvalid += w_ok[ns] ? 1 : 0;
+          }
+          const int hw = p.conv_h * p.conv_w;
+          const long long pm0 = (long long)kb0 * GEMM_BLOCK_K;
+          w_pb = (int)(pm0 / hw);
+          const int prem = (int)(pm0 - (long long)w_pb * hw);
+          w_py = prem / p.conv_w;
+          w_px = prem - w_py * p.conv_w;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const long long t0_ = (kProf && p.prof) ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -291,13 +326,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (!nn_conv) mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           if (nn_conv) {
           } else if (p.conv) {
-            const int tap = kb / cbt;
-            const int cbi = kb - tap * cbt;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            const int ix = cv_x * p.conv_stride + kx - 1;
-            const int iy = cv_y * p.conv_stride + ky - 1;
-            if (cbi < p.conv_cb0) tma_load_4d(sa, &tmap_a, full_bar(stage), cbi * 64, ix, iy, cv_b);
-            else tma_load_4d(sa, &tmap_a2, full_bar(stage), (cbi - p.conv_cb0) * 64, ix, iy, cv_b);
+            const int ix = cv_x * p.conv_stride + f_kx - 1;
+            const int iy = cv_y * p.conv_stride + f_ky - 1;
+            if (f_cbi < p.conv_cb0) tma_load_4d(sa, &tmap_a, full_bar(stage), f_cbi * 64, ix, iy, cv_b);
+            else tma_load_4d(sa, &tmap_a2, full_bar(stage), (f_cbi - p.conv_cb0) * 64, ix, iy, cv_b);
+            if (++f_cbi == cbt) {
+              f_cbi = 0;
+              if (++f_kx == 3) { f_kx = 0; ++f_ky; }
+            }
           } else
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
 #pragma unroll
@@ -306,26 +342,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (p.conv) {
               // weight gradient of a 3x3 conv: k = output pixel, n = (tap, input channel); the B box is the input map
               // shifted by the tap (TMA 4-D tile of 64 pixels x 64 channels, zero fill = padding)
-              const int hw = p.conv_h * p.conv_w;
-              const int pm0 = kb * GEMM_BLOCK_K;
-              const int pb = pm0 / hw, prem = pm0 - pb * hw;
-              const int py0 = prem / p.conv_w, px0 = prem - py0 * p.conv_w;
-              int nvalid = 0;
-#pragma unroll
-              for (int ns = 0; ns < BLOCK_N / 64; ++ns) nvalid += (n_blk * (BLOCK_N / 64) + ns) < 9 * cbt ? 1 : 0;
-              mbar_expect_tx(full_bar(stage), Cfg::kABytes + nvalid * 8192);
+              mbar_expect_tx(full_bar(stage), Cfg::kABytes + w_nvalid * 8192);
               tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BLOCK_K, m0);
 #pragma unroll
-              for (int ns = 0; ns < BLOCK_N / 64; ++ns) {
-                const int nb = n_blk * (BLOCK_N / 64) + ns;
-                if (nb < 9 * cbt) {
-                  const int tap = nb / cbt, cbi = nb - tap * cbt;
-                  const int ky = tap / 3, kx = tap - ky * 3;
-                  const int ix = px0 * p.conv_stride + kx - 1, iy = py0 * p.conv_stride + ky - 1;
-                  if (cbi < p.conv_cb0) tma_load_4d(sb + ns * 8192, &tmap_b, full_bar(stage), cbi * 64, ix, iy, pb);
-                  else tma_load_4d(sb + ns * 8192, &tmap_a2, full_bar(stage), (cbi - p.conv_cb0) * 64, ix, iy, pb);
+              for (int ns = 0; ns < NSL; ++ns) {
+                if (w_ok[ns]) {
+                  const int ix = w_px * p.conv_stride + w_dx[ns], iy = w_py * p.conv_stride + w_dy[ns];
+                  tma_load_4d(sb + ns * 8192, w_src[ns] ? &tmap_a2 : &tmap_b, full_bar(stage), w_c[ns], ix, iy, w_pb);
                 }
               }
+              // next 64-pixel window (full rows when the map is narrower than 64 pixels)
+              if (p.conv_w >= GEMM_BLOCK_K) {
+                w_px += GEMM_BLOCK_K;
+                if (w_px >= p.conv_w) { w_px = 0; ++w_py; }
+              } else {
+                w_py += p.conv_rows_per_kb;
+              }
+              if (w_py >= p.conv_h) { w_py = 0; ++w_pb; }
             } else {
 #pragma unroll
             for (int ns = 0; ns < BLOCK_N / 64; ++ns)
@@ -348,6 +381,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      // descriptors of stage 0; the start-address field counts 16-byte units, so stage / k offsets are plain adds
+      // (this single thread issues every MMA: with small tiles its instruction count per k block is the bottleneck)
+      const uint64_t da0 = umma_desc_sw128(smem_base);
+      const uint64_t db0 = MODE == MV_GEMM_NN_ATOMIC
+                               ? umma_desc_sw128(smem_base + Cfg::kABytes, 1024, 8192)  // MN-major: 64-column atoms 8 KB apart
+                               : umma_desc_sw128(smem_base + Cfg::kABytes);
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int split = tile / num_mn;
         const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
@@ -361,21 +400,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(full_bar(stage), phase);
           if (kProf && p.prof) prof_acc[1] += clock64() - t0_;
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sb);
+          const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
+          const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             if constexpr (MODE == MV_GEMM_HEAD_CONV) {
               umma_bf16(d_tmem + kb * 16, da + 2 * k, db + 2 * k, idesc, k != 0);
             } else if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
-              constexpr uint32_t idesc_mn = umma_idesc_bf16(GEMM_BLOCK_M, 64, 0, 1);
-#pragma unroll
-              for (int ns = 0; ns < BLOCK_N / 64; ++ns)
-                umma_bf16(d_tmem + ns * 64, da + 2 * k, umma_desc_sw128(sb + ns * 8192 + k * 2048, 1024, 1024), idesc_mn,
-                          (kb != kb0) || (k != 0));
+              // B is MN-major: 16 reduction rows = 2 KB per k step; all BLOCK_N columns (64-column swizzle atoms,
+              // leading-dimension offset 8 KB) in ONE instruction
+              constexpr uint32_t idesc_mn = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 1);
+              umma_bf16(d_tmem, da + 2 * k, db + (2048 >> 4) * k, idesc_mn, (kb != kb0) || (k != 0));
             } else if constexpr (PAIR) {
               umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
             } else {
@@ -505,6 +541,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld32(taddr + egrp * 32, v);
 #pragma unroll 1
         for (int c = egrp; c < NC; c += EGRPS) {
+          // GATE_MASK: the per-(row, head) gate gradients of this chunk, fetched before the TMEM wait (hidden latency)
+          float du4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.act == MV_ACT_GATE_MASK) {
+            const int nnm = n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int mm = m_warp + it * 8 + (lane >> 2);
+              if (mm < p.m && nnm < p.n)
+                du4[it] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nnm >> 4)]);
+            }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -592,7 +639,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   if (p.act == MV_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
                 }
                 if (p.act == MV_ACT_GATE_MASK) {  // e = du[m, head] where the (batch-normalised) unit is active
-                  const float du = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nn >> 4)]);
+                  const float du = du4[it];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? du : 0.f;
                 }
@@ -954,6 +1001,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.conv_h = a.conv_h; p.conv_w = a.conv_w;
   p.conv_tw = a.conv_w < 128 ? a.conv_w : 128;
   p.conv_stride = a.conv_stride;
+  p.conv_rows_per_kb = (a.conv && a.conv_w > 0 && a.conv_w < GEMM_BLOCK_K) ? GEMM_BLOCK_K / a.conv_w : 1;
   p.conv_cb0 = (a.conv_c0 + 63) / 64;
   p.conv_cb1 = (a.conv_c1 + 63) / 64;
 
