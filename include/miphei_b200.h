@@ -150,6 +150,11 @@ int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, float* l
  *   mv_upsample2x     Fusion_Block's bilinear x2 (mipheivit.py:89), NHWC bf16.
  * ---------------------------------------------------------------------------------------------------------- */
 int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk, void* stream);
+/* Input staging for whole-slide inference: raw uint8 H&E tiles NHWC [batch, size, size, 3] normalised on the
+ * device, v = u8 * scale[c] + bias[c] with the H-Optimus statistics of src/dataset.py:600-601 (scale = 1/(255 std_c),
+ * bias = -mean_c/std_c; HOST pointers to 3 floats each) — the H2D copy is 4x smaller than the fp32 NCHW tensor. */
+int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const float* bias3, void* img_nhwc8, void* patch_matrix,
+                     int batch, int size, int ldk, void* stream);
 int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int batch, int n_tok, int n_prefix, int dim, void* stream);
 int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid, int target,
                      int dim, void* stream);

@@ -11,24 +11,40 @@
 
 namespace mv {
 
-__global__ void prep_image_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ img, int B, int S) {
+// Input pixel (b, c, y, x): fp32 NCHW (already normalised, the reference's DataLoader output) or raw uint8 NHWC H&E tiles
+// normalised here with the H-Optimus statistics of src/dataset.py:600-601, v = u8 * scale[c] + bias[c].
+struct InNorm {
+  float scale[3], bias[3];
+};
+template <bool U8>
+__device__ __forceinline__ float in_px(const void* x, const InNorm& nm, long long b, int c, int y, int xx, int S) {
+  if (U8) {
+    const uint8_t u = reinterpret_cast<const uint8_t*>(x)[((b * S + y) * (long long)S + xx) * 3 + c];
+    return (float)u * nm.scale[c] + nm.bias[c];
+  }
+  return reinterpret_cast<const float*>(x)[((b * 3 + c) * S + y) * (long long)S + xx];
+}
+
+template <bool U8>
+__global__ void prep_image_kernel(const void* __restrict__ x, InNorm nm, __nv_bfloat16* __restrict__ img, int B, int S) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const long long npix = (long long)B * S * S;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const long long plane = (long long)S * S;
   const long long b = i / plane, r = i - b * plane;
-  const float* xb = x + b * 3 * plane + r;
+  const int y = (int)(r / S), xx = (int)(r - (long long)y * S);
   uint4 o;
-  o.x = pack_bf16x2(xb[0], xb[plane]);
-  o.y = pack_bf16x2(xb[2 * plane], 0.f);
+  o.x = pack_bf16x2(in_px<U8>(x, nm, b, 0, y, xx, S), in_px<U8>(x, nm, b, 1, y, xx, S));
+  o.y = pack_bf16x2(in_px<U8>(x, nm, b, 2, y, xx, S), 0.f);
   o.z = 0u;
   o.w = 0u;
   reinterpret_cast<uint4*>(img)[i] = o;
 }
 
-__global__ void patch_matrix_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int S, int g,
-                                    int ldk) {
+template <bool U8>
+__global__ void patch_matrix_kernel(const void* __restrict__ x, InNorm nm, __nv_bfloat16* __restrict__ a, int B, int S,
+                                    int g, int ldk) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   // one thread per (patch row, 8-wide k group); ldk = 592
   const int groups = ldk / 8;
@@ -45,7 +61,7 @@ __global__ void patch_matrix_kernel(const float* __restrict__ x, __nv_bfloat16* 
     const int k = kg * 8 + j;
     if (k < 588) {
       const int c = k / 196, rr = k - c * 196, ky = rr / 14, kx = rr - ky * 14;
-      f[j] = x[((b * 3 + c) * S + (py * 14 + ky)) * (long long)S + px * 14 + kx];
+      f[j] = in_px<U8>(x, nm, b, c, py * 14 + ky, px * 14 + kx, S);
     } else {
       f[j] = 0.f;
     }
@@ -219,26 +235,48 @@ extern "C" int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int ba
   return MV_OK;
 }
 
-extern "C" int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
-                             void* stream_) {
-  using namespace mv;
-  MV_CHECK_ARG(x && batch > 0 && size >= 14, "mv_prep_input: null/empty");
-  MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input: patch matrix pitch must be 592");
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+namespace mv {
+template <bool U8>
+static int launch_prep(const void* x, const InNorm& nm, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
+                       cudaStream_t stream) {
   if (img_nhwc8) {
     const long long npix = (long long)batch * size * size;
-    MV_LAUNCH(prep_image_kernel, (unsigned)((npix + 255) / 256), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(img_nhwc8),
-                                                                          batch, size);
+    MV_LAUNCH(prep_image_kernel<U8>, (unsigned)((npix + 255) / 256), 256, 0, stream, x, nm,
+              reinterpret_cast<__nv_bfloat16*>(img_nhwc8), batch, size);
     MV_CHECK_LAUNCH("prep_image");
   }
   if (patch_matrix) {
     const int g = size / 14;
     const long long total = (long long)batch * g * g * (ldk / 8);
-    MV_LAUNCH(patch_matrix_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
-        x, reinterpret_cast<__nv_bfloat16*>(patch_matrix), batch, size, g, ldk);
+    MV_LAUNCH(patch_matrix_kernel<U8>, (unsigned)((total + 255) / 256), 256, 0, stream, x, nm,
+              reinterpret_cast<__nv_bfloat16*>(patch_matrix), batch, size, g, ldk);
     MV_CHECK_LAUNCH("patch_matrix");
   }
   return MV_OK;
+}
+}  // namespace mv
+
+extern "C" int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
+                             void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(x && batch > 0 && size >= 14, "mv_prep_input: null/empty");
+  MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input: patch matrix pitch must be 592");
+  InNorm nm = {{1.f, 1.f, 1.f}, {0.f, 0.f, 0.f}};
+  return launch_prep<false>(x, nm, img_nhwc8, patch_matrix, batch, size, ldk, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// raw uint8 H&E tiles, NHWC [B, S, S, 3]; v = u8 * scale[c] + bias[c] (scale = 1 / (255 std_c), bias = -mean_c / std_c)
+extern "C" int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const float* bias3, void* img_nhwc8,
+                                void* patch_matrix, int batch, int size, int ldk, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(tiles_u8 && scale3 && bias3 && batch > 0 && size >= 14, "mv_prep_input_u8: null/empty");
+  MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input_u8: patch matrix pitch must be 592");
+  InNorm nm;
+  for (int c = 0; c < 3; ++c) {
+    nm.scale[c] = scale3[c];  // HOST pointers: six constants passed by value to the kernels
+    nm.bias[c] = bias3[c];
+  }
+  return launch_prep<true>(tiles_u8, nm, img_nhwc8, patch_matrix, batch, size, ldk, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid,

@@ -231,6 +231,7 @@ class MipheiEngine:
             self._pack_trainable()
             for ws in self._ws.values():
                 ws.graph = None  # re-capture after a weight update (packed tensors are re-created)
+                ws.__dict__.pop("graphs", None)
                 if hasattr(ws, "graph_u8"):
                     ws.graph_u8 = None
 
@@ -242,9 +243,12 @@ class MipheiEngine:
         return ws
 
     # ------------------------------------------------------------------ forward pieces (eval)
-    def _encode_tokens(self, ws):
+    def _encode_tokens(self, ws, u8_in=False):
         B, N, D, g = ws.B, self.N, self.D, self.g
-        ops.prep_input(ws.x_in, img=ws.img8, pm=ws.pm)
+        if u8_in:  # raw uint8 NHWC tiles, normalised on the device
+            ops.prep_input_u8(ws.x_u8, img=ws.img8, pm=ws.pm)
+        else:
+            ops.prep_input(ws.x_in, img=ws.img8, pm=ws.pm)
         ops.fill_prefix(ws.x, self.prefix, B, N)
         ops.gemm(ws.pm, self.pe_w, shift=self.pe_b, resid=self.pos, out=ws.x, rows_per_group=g * g, group_stride=N,
                  row_offset=NUM_PREFIX, resid_row_mod=True)
@@ -285,9 +289,87 @@ class MipheiEngine:
                  shift=hd["gate_shift"], in2=hd["gate_w2"], resid=hd["gate_b2"], out=ws.gate)
         ops.gemm(f, hd["conv_w"], mode=ops.GEMM_HEAD_CONV, conv=dict(stride=1), shift=hd["conv_b"], in2=ws.gate, out=out)
 
-    def _run_eval(self, ws, out):
-        self._encode_tokens(ws)
+    def _run_eval(self, ws, out, u8_in=False):
+        self._encode_tokens(ws, u8_in)
         self._decode_maps(ws, out)
+
+    def _graph_for(self, ws, out_buf, key, u8_in):
+        """Captured forward of one workspace (one graph per output kind / input kind); warm-up run outside capture."""
+        graphs = ws.__dict__.setdefault("graphs", {})
+        gr = graphs.get(key)
+        if gr is None:
+            self._run_eval(ws, out_buf, u8_in)  # module load, descriptor creation, smem attribute calls
+            torch.cuda.current_stream().synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._run_eval(ws, out_buf, u8_in)
+            graphs[key] = gr
+        return gr
+
+    @torch.no_grad()
+    def infer_stream(self, batches, out_dtype=torch.uint8, depth=2):
+        """Whole-slide style inference over an iterable of PINNED host batches — fp32 NCHW normalised tiles (the
+        reference's DataLoader output) or raw uint8 NHWC tiles (normalised on the device) — yielding pinned host
+        predictions [B, C, S, S] (uint8 sink of src/callbacks.py:345-346 by default, or fp32).
+
+        Double-buffered: the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams while batch i
+        computes (one captured graph per buffer). A yielded tensor is reused `depth` batches later: consume it first."""
+        self._ensure_packed()
+        assert out_dtype in (torch.uint8, torch.float32)
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_io_streams"):
+            self._io_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_run, s_out = self._io_streams
+        slots = {}
+        pending = []  # (event, host tensor) in submission order
+        ev_free = {}  # slot -> event: its output buffer has been copied out (the slot may run again)
+        i = 0
+        for xb in batches:
+            B = xb.shape[0]
+            u8_in = xb.dtype == torch.uint8
+            if u8_in:
+                assert xb.dim() == 4 and xb.shape[3] == 3 and xb.shape[1] == self.S and xb.shape[2] == self.S
+            else:
+                self._check_input_shape(xb)
+            k = (B, i % depth)
+            if k not in slots:
+                ws = self._workspace(B, 100 + i % depth)
+                if u8_in and not hasattr(ws, "x_u8"):
+                    ws.x_u8 = torch.empty((B, self.S, self.S, 3), dtype=torch.uint8, device=dev)
+                dev_out = torch.empty((B, self.heads_out, self.S, self.S), dtype=out_dtype, device=dev)
+                host_out = torch.empty((B, self.heads_out, self.S, self.S), dtype=out_dtype).pin_memory()
+                slots[k] = (ws, dev_out, host_out)
+            ws, dev_out, host_out = slots[k]
+            if k in ev_free:
+                s_in.wait_event(ev_free[k])  # previous use of this slot fully drained (input consumed, output copied)
+            else:
+                s_in.wait_stream(cur)
+            with torch.cuda.stream(s_in):
+                (ws.x_u8 if u8_in else ws.x_in).copy_(xb, non_blocking=True)
+                e_in = torch.cuda.Event()
+                e_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(e_in)
+                self._graph_for(ws, dev_out, ("stream", out_dtype, u8_in), u8_in).replay()
+                e_run = torch.cuda.Event()
+                e_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e_run)
+                host_out.copy_(dev_out, non_blocking=True)
+                e_out = torch.cuda.Event()
+                e_out.record(s_out)
+            ev_free[k] = e_out
+            pending.append((e_out, host_out))
+            i += 1
+            if len(pending) >= depth:
+                e, h = pending.pop(0)
+                e.synchronize()
+                yield h
+        for e, h in pending:
+            e.synchronize()
+            yield h
+        cur.wait_stream(s_out)
 
     # ------------------------------------------------------------------ public entry points
     def _out_dtype(self, x):
@@ -295,11 +377,14 @@ class MipheiEngine:
             return torch.get_autocast_dtype("cuda")
         return x.dtype if x.dtype in (torch.float16, torch.bfloat16) else torch.float32
 
+    def _check_input_shape(self, x):
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.S or x.shape[3] != self.S:
+            raise AssertionError("Input size (%s) doesn't match model (%d)" % (tuple(x.shape), self.S))
+
     def _check_input(self, x):
         if not x.is_cuda:
             raise ops._lib.MipheiB200Error("MIPHEI-ViT B200 generator needs CUDA inputs (got %s); no CPU path" % x.device)
-        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.S or x.shape[3] != self.S:
-            raise AssertionError("Input size (%s) doesn't match model (%d)" % (tuple(x.shape), self.S))
+        self._check_input_shape(x)
 
     def forward(self, x):
         self._ensure_packed(train=self.model.training)

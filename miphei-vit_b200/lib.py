@@ -56,6 +56,8 @@ _SIGNATURES = {
                                  c_void_p, c_i64, c_int, c_int, c_float, c_void_p]),
     "mv_attn_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "mv_prep_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv_prep_input_u8": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p, c_int, c_int,
+                                 c_int, c_void_p]),
     "mv_fill_prefix": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_tokens_to_map": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -189,6 +189,26 @@ def prep_input(x, want_image=True, want_patches=True, img=None, pm=None):
     return img, pm
 
 
+HOPTIMUS_MEAN = (0.707223, 0.578729, 0.703617)  # src/dataset.py:601
+HOPTIMUS_STD = (0.211883, 0.230117, 0.177517)
+
+
+def prep_input_u8(tiles, img=None, pm=None, mean=HOPTIMUS_MEAN, std=HOPTIMUS_STD, want_image=True, want_patches=True):
+    """raw uint8 NHWC tiles [B, S, S, 3] -> (NHWC bf16 image, patch matrix), normalised on the device (mv_prep_input_u8)."""
+    lib = _lib_for(tiles)
+    assert tiles.dtype == torch.uint8 and tiles.is_contiguous() and tiles.dim() == 4 and tiles.shape[3] == 3
+    B, S = tiles.shape[0], tiles.shape[1]
+    g = S // 14
+    if img is None and want_image:
+        img = torch.empty((B, S, S, 8), dtype=torch.bfloat16, device=tiles.device)
+    if pm is None and want_patches:
+        pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=tiles.device)
+    sc = (ctypes.c_float * 3)(*[1.0 / (255.0 * s) for s in std])
+    bi = (ctypes.c_float * 3)(*[-m / s for m, s in zip(mean, std)])
+    _lib.check(lib.mv_prep_input_u8(_ptr(tiles), sc, bi, _ptr(img), _ptr(pm), B, S, 592, _stream()), "mv_prep_input_u8")
+    return img, pm
+
+
 def fill_prefix(x_res, prefix, batch, n_tok):
     lib = _lib_for(x_res)
     assert x_res.dtype == torch.float32 and prefix.dtype == torch.float32 and prefix.is_contiguous()

@@ -109,6 +109,32 @@ def test_lora_folded_into_qkv_matches_explicit_lora_path():
     assert not torch.allclose(got2, folded)
 
 
+def test_streamed_inference_float_and_uint8_tiles():
+    """engine.infer_stream: double-buffered H2D / compute / D2H over pinned host batches; fp32 normalised tiles and raw
+    uint8 NHWC tiles (normalised on the device with the constants of src/dataset.py:600-601) give the predictions of the
+    plain call, in submission order."""
+    cfg = om.Config(img_size=128, embed_dim=128, depth=2, num_heads=2, hidden=256, out_chans=3)
+    sd = om.init_state_dict(cfg, seed=11, perturb=True)
+    model = build(cfg, sd)
+    u8s = [om.synthetic_tiles_u8(2, cfg.img_size, seed=40 + i) for i in range(5)]  # [B, 3, S, S] uint8 values
+    xs = [om.normalize_tiles(u) for u in u8s]
+    with torch.no_grad():
+        refs = [model(x.cuda()).float().cpu() for x in xs]
+        ref8 = [model.engine.infer(x.cuda(), out_dtype=torch.uint8).cpu() for x in xs]
+    outs = [o.clone() for o in model.engine.infer_stream([x.pin_memory() for x in xs], out_dtype=torch.float32)]
+    assert len(outs) == 5
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    outs8 = [o.clone() for o in model.engine.infer_stream([x.pin_memory() for x in xs])]
+    for o, r in zip(outs8, ref8):
+        assert torch.equal(o, r)
+    raw = [u.permute(0, 2, 3, 1).contiguous().to(torch.uint8).pin_memory() for u in u8s]  # NHWC uint8
+    outs_raw = [o.clone() for o in model.engine.infer_stream(raw, out_dtype=torch.float32)]
+    for o, r in zip(outs_raw, refs):
+        check_pred(o, r)
+        assert (o - r).abs().max().item() < 2e-2  # normalisation rounding order only (fp32 -> bf16 inputs)
+
+
 def test_cpu_input_fails_loudly():
     cfg = om.Config(img_size=128, embed_dim=128, depth=1, num_heads=2, hidden=256, out_chans=2)
     model = build(cfg, om.init_state_dict(cfg, seed=1))
