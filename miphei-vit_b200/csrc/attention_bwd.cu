@@ -199,14 +199,22 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
         dsum_r = p.dsum[vec0 + orow];
       }
+      // DKV: per-column (query) statistics of an inner tile — threads 0..63 carry lse * log2(e), threads 64..127 D — are
+      // fetched ONE TILE AHEAD into a register, so the global-load latency is not on the per-tile critical path
+      auto load_stat = [&](int ib) {
+        const int q = ib * 64 + (tid & 63);
+        if (q >= n_tok) return 0.f;
+        return tid < 64 ? p.lse[vec0 + q] * 1.4426950408889634f : p.dsum[vec0 + q];
+      };
+      float stat_next = DKV ? load_stat(0) : 0.f;
       for (int ib = 0; ib < ncb; ++ib, ++itn) {
         const float* sl = s_lse + (itn & 1) * 64;
         const float* sd = s_dsum + (itn & 1) * 64;
-        if (DKV) {  // per-column (query) statistics of this inner tile, double buffered
-          const int q = ib * 64 + (tid & 63);
-          if (tid < 64) s_lse[(itn & 1) * 64 + tid] = q < n_tok ? p.lse[vec0 + q] * 1.4426950408889634f : 0.f;
-          else s_dsum[(itn & 1) * 64 + tid - 64] = q < n_tok ? p.dsum[vec0 + q] : 0.f;
+        if (DKV) {  // double-buffered smem copy of this tile's statistics
+          if (tid < 64) s_lse[(itn & 1) * 64 + tid] = stat_next;
+          else s_dsum[(itn & 1) * 64 + tid - 64] = stat_next;
           nbar(1, 128);
+          if (ib + 1 < ncb) stat_next = load_stat(ib + 1);
         }
         mbar_wait(bar_xy, xph);
         tc_fence_after();

@@ -8,11 +8,6 @@
 
 namespace mv {
 
-#ifndef MV_SPIN_LIMIT
-// A wait that spins this many times is treated as a deadlock: the kernel traps instead of hanging the GPU.
-#define MV_SPIN_LIMIT (1u << 26)
-#endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -59,21 +54,38 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
       "r"(cta_rank)
       : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots consumed) until the phase completes
+// or the hint expires — a plain try_wait returned after a few hundred cycles, and the polling loops of the single-thread
+// TMA / MMA warps were issuing as many instructions as the math warps they share a scheduler with.
+#ifndef MV_WAIT_HINT_NS
+#define MV_WAIT_HINT_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(done)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(MV_WAIT_HINT_NS)
       : "memory");
   return done != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A wait that lasts longer than MV_WAIT_TIMEOUT_NS is treated as a deadlock: the kernel traps instead of hanging the GPU.
+#ifndef MV_WAIT_TIMEOUT_NS
+#define MV_WAIT_TIMEOUT_NS 4000000000ull
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > MV_SPIN_LIMIT) __trap();
+    if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > MV_WAIT_TIMEOUT_NS) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
