@@ -143,14 +143,19 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       uint32_t rph = 0, cph = 0, xph = 0, aph = 0;
       const uint32_t idesc_xy = umma_idesc_bf16(128, 64);
       const uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
+      // all smem descriptors are built once: this single thread sits on the per-tile critical path
+      // (XY MMAs -> math -> accumulate MMAs), so its instruction count per tile matters
+      const uint64_t dr1 = umma_desc_sw128(sR), dr2 = umma_desc_sw128(sR + ATB_RTILE);
+      const uint64_t dk1 = umma_desc_sw128(sC), dk2 = umma_desc_sw128(sC + ATB_CTILE);                            // K-major
+      const uint64_t dm1 = umma_desc_sw128(sC, 1024, 1024), dm2 = umma_desc_sw128(sC + ATB_CTILE, 1024, 1024);  // MN-major
+      constexpr uint64_t kStageStep = (2 * ATB_CTILE) >> 4;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(r_full, rph);
-        const uint64_t dr1 = umma_desc_sw128(sR), dr2 = umma_desc_sw128(sR + ATB_RTILE);
         for (int ib = 0; ib < ncb; ++ib) {
           mbar_wait(c_full(cs), cph);
           tc_fence_after();
-          const uint32_t c1 = sC + cs * 2 * ATB_CTILE, c2 = c1 + ATB_CTILE;
-          const uint64_t dc1 = umma_desc_sw128(c1), dc2 = umma_desc_sw128(c2);
+          const uint64_t so = cs ? kStageStep : 0;
+          const uint64_t dc1 = dk1 + so, dc2 = dk2 + so;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_X, dr1 + 2 * k, dc1 + 2 * k, idesc_xy, k != 0);
 #pragma unroll
@@ -160,13 +165,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
           if (ib == 0) mbar_wait(acc_empty, aph ^ 1);  // previous item's accumulators drained
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile
-            if (DKV) {
-              const uint64_t dmn2 = umma_desc_sw128(c2 + k * 2048, 1024, 1024);
-              umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + k * 8, dmn2, idesc_acc, (ib | k) != 0);
-            }
-            const uint64_t dmn1 = umma_desc_sw128(c1 + k * 2048, 1024, 1024);
-            umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + k * 8, dmn1, idesc_acc, (ib | k) != 0);
+          for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile; 16 reduction rows = 2 KB per step
+            if (DKV) umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + k * 8, dm2 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
+            umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + k * 8, dm1 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
           }
           umma_commit(c_empty(cs));
           if (ib == ncb - 1) {
@@ -219,12 +220,17 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         mbar_wait(bar_xy, xph);
         tc_fence_after();
         uint32_t pp[2][16], pd[2][16];
+        uint32_t xs[2][32], ys[2][32];  // one TMEM round trip for the whole 64-column tile row
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          uint32_t x[32], y[32];
-          tmem_ld32(trow + COL_X + ci * 32, x);
-          tmem_ld32(trow + COL_Y + ci * 32, y);
-          tmem_ld_wait();
+          tmem_ld32(trow + COL_X + ci * 32, xs[ci]);
+          tmem_ld32(trow + COL_Y + ci * 32, ys[ci]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const uint32_t* x = xs[ci];
+          const uint32_t* y = ys[ci];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float pv[2], dv[2];
