@@ -227,26 +227,47 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
           tmem_ld32(trow + COL_Y + ci * 32, ys[ci]);
         }
         tmem_ld_wait();
+        // dS is formed WITHOUT the softmax scale (applied once per item to the accumulator in the epilogue), and tiles
+        // that lie completely inside the sequence skip the per-element bounds predicates
+        const bool interior = (ob * 128 + 127 < n_tok) && (ib * 64 + 63 < n_tok);  // CTA-uniform
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const uint32_t* x = xs[ci];
           const uint32_t* y = ys[ci];
+          if (interior) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float pv[2], dv[2];
+            for (int j = 0; j < 16; ++j) {
+              float pv[2], dv[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = ci * 32 + 2 * j + e;
-              const int icol = ib * 64 + col;
-              const bool ok = orow < n_tok && icol < n_tok;
-              const float l2 = DKV ? sl[col] : lse_r;
-              const float dd = DKV ? sd[col] : dsum_r;
-              const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
-              pv[e] = pr;
-              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd) * p.scale;
+              for (int e = 0; e < 2; ++e) {
+                const int col = ci * 32 + 2 * j + e;
+                const float l2 = DKV ? sl[col] : lse_r;
+                const float dd = DKV ? sd[col] : dsum_r;
+                const float pr = ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2);
+                pv[e] = pr;
+                dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
+              }
+              pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
+              pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
             }
-            pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
-            pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float pv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int col = ci * 32 + 2 * j + e;
+                const int icol = ib * 64 + col;
+                const bool ok = orow < n_tok && icol < n_tok;
+                const float l2 = DKV ? sl[col] : lse_r;
+                const float dd = DKV ? sd[col] : dsum_r;
+                const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
+                pv[e] = pr;
+                dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
+              }
+              pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
+              pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
+            }
           }
         }
         // every column of this row has been read (this warp is the only reader of its lanes): P / dS overwrite X / Y
@@ -275,28 +296,28 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       mbar_arrive(acc_empty);
       if (orow < n_tok) {
         __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + h * 64;
-        auto store64 = [&](__nv_bfloat16* dst, const uint32_t* lo, const uint32_t* hi) {
+        auto store64 = [&](__nv_bfloat16* dst, const uint32_t* lo, const uint32_t* hi, float mul) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(lo[8 * j + 0]), __uint_as_float(lo[8 * j + 1]));
-            u.y = pack_bf16x2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3]));
-            u.z = pack_bf16x2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5]));
-            u.w = pack_bf16x2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7]));
+            u.x = pack_bf16x2(__uint_as_float(lo[8 * j + 0]) * mul, __uint_as_float(lo[8 * j + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(lo[8 * j + 2]) * mul, __uint_as_float(lo[8 * j + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(lo[8 * j + 4]) * mul, __uint_as_float(lo[8 * j + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(lo[8 * j + 6]) * mul, __uint_as_float(lo[8 * j + 7]) * mul);
             reinterpret_cast<uint4*>(dst)[j] = u;
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(hi[8 * j + 0]), __uint_as_float(hi[8 * j + 1]));
-            w.y = pack_bf16x2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3]));
-            w.z = pack_bf16x2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5]));
-            w.w = pack_bf16x2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7]));
+            w.x = pack_bf16x2(__uint_as_float(hi[8 * j + 0]) * mul, __uint_as_float(hi[8 * j + 1]) * mul);
+            w.y = pack_bf16x2(__uint_as_float(hi[8 * j + 2]) * mul, __uint_as_float(hi[8 * j + 3]) * mul);
+            w.z = pack_bf16x2(__uint_as_float(hi[8 * j + 4]) * mul, __uint_as_float(hi[8 * j + 5]) * mul);
+            w.w = pack_bf16x2(__uint_as_float(hi[8 * j + 6]) * mul, __uint_as_float(hi[8 * j + 7]) * mul);
             reinterpret_cast<uint4*>(dst)[4 + j] = w;
           }
         };
         if (DKV) {
-          store64(base + p.dim, a0, a1);      // dK  (acc2 = dS^T Q)
-          store64(base + 2 * p.dim, b0, b1);  // dV  (acc1 = P^T dO)
+          store64(base + p.dim, a0, a1, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
+          store64(base + 2 * p.dim, b0, b1, 1.f);  // dV = P^T dO                        (acc1)
         } else {
-          store64(base, a0, a1);              // dQ  (acc2 = dS K)
+          store64(base, a0, a1, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
         }
       }
       aph ^= 1;
