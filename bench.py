@@ -287,7 +287,11 @@ def run_cuda(args):
         ach = flops / dur / 1e9
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel<256, SWIGLU> (fc1 + SwiGLU epilogue)",
                 "achieved": ach, "peak": pk["tc_sus"], "unit": "TFLOP/s", "frac": ach / pk["tc_sus"],
-                "peak_kind": "%s sustained cuBLAS bf16 (burst %.1f)" % (pk["source"], pk["tc"]), "traffic": None,
+                "peak_kind": "%s sustained cuBLAS bf16 (burst %.1f)" % (pk["source"], pk["tc"]),
+                # DRAM bytes of ONE launch of this kernel at M=5264 from the committed ncu --set full capture
+                # (profiles/r01_ncu_full_encoder_kernels_infer_b16_v3.csv: 41.4 MB read + 11.9 MB written)
+                "traffic": 53.3e6 if ws.M == 5264 else None, "traffic_unit": "B/launch (ncu dram__bytes_read+write)",
+                "algorithmic_bytes": float(2 * (ws.M * eng.D + 2 * eng.H * eng.D + ws.M * eng.H)),
                 "launch_us": dur * 1e3, "flops_per_launch": flops,
                 "whole_step_tflops": world * B * GF_PER_TILE_FWD / ms_step,
                 "whole_step_frac_of_sustained": B * GF_PER_TILE_FWD / ms_step / pk["tc_sus"]}
