@@ -241,6 +241,24 @@ int mv_heads_ds(const float* dpred, const float* pred, void* ds, float* dbias, i
 int mv_heads_bwd_stencil(const void* t, const void* ds, const void* gate, void* dt, void* du, float* db2, int batch, int h,
                          int w, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-nucleus mean intensities: MeanCellExtrator.extract_mean, src/utils.py:49-121 (and the same
+ * reduction in CellMetrics.update, src/metrics.py:32-74).  pred / target fp32 NCHW [batch, chans, hw]; nuclei labels
+ * [batch, hw] int32 or int64 (label_bytes 4 / 8), 0 = background.  One CTA per image (csrc/cell_means.cu).
+ *   mv_cell_means       per image: ids (ascending, like torch.unique), means_pred / means_target [batch, cap, chans],
+ *                       counts [batch, cap], n_unique [batch]; rows >= n_unique[b] are untouched. cap = power of two
+ *                       >= the number of nuclei of any image; *overflow is set to 1 if an image has more (the caller
+ *                       must pre-zero it and re-run with a larger cap).  target / means_target may both be NULL.
+ *   mv_cell_means_pack  concatenates the per-image rows in batch order (the reference's torch.cat): out_* hold
+ *                       sum(n_unique) rows.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_cell_means(const float* pred, const float* target, const void* nuclei, int label_bytes, int batch, int chans, int hw,
+                  int cap, float* means_pred, float* means_target, int64_t* ids, float* counts, int32_t* n_unique,
+                  int32_t* overflow, void* stream);
+int mv_cell_means_pack(const float* means_pred, const float* means_target, const int64_t* ids, const float* counts,
+                       const int32_t* n_unique, int batch, int chans, int cap, float* out_pred, float* out_target,
+                       int64_t* out_ids, float* out_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -451,3 +451,44 @@ def heads_bwd_stencil(t, ds, gate, B, H, W, db2, dt=None, du=None):
     _lib.check(lib.mv_heads_bwd_stencil(_ptr(t), _ptr(ds), _ptr(gate), _ptr(dt), _ptr(du), _ptr(db2), B, H, W, _stream()),
                "mv_heads_bwd_stencil")
     return dt, du
+
+
+def cell_means(pred, target, nuclei, cap=1024, return_counts=False):
+    """Per-nucleus mean intensities (mv_cell_means + mv_cell_means_pack): pred / target fp32 [B, C, H, W] (target may be
+    None), nuclei integer labels [B, H, W] or [B, 1, H, W], 0 = background.  Returns (pred_means [n, C], target_means
+    [n, C] or None, cell_ids [n] int64, n_unique [B] int32) with the rows of image 0 first and ids ascending per image —
+    the layout of MeanCellExtrator.extract_mean (src/utils.py:49-121).  One host sync (the row count)."""
+    lib = _lib_for(pred)
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 4
+    B, C, H, W = pred.shape
+    if target is not None:
+        assert target.dtype == torch.float32 and target.is_contiguous() and target.shape == pred.shape
+    nuclei = nuclei.reshape(B, H * W)
+    if nuclei.dtype not in (torch.int32, torch.int64):
+        nuclei = nuclei.long()
+    nuclei = nuclei.contiguous()
+    dev = pred.device
+    while True:
+        mp = torch.empty((B, cap, C), dtype=torch.float32, device=dev)
+        mt = torch.empty((B, cap, C), dtype=torch.float32, device=dev) if target is not None else None
+        ids = torch.empty((B, cap), dtype=torch.int64, device=dev)
+        cnt = torch.empty((B, cap), dtype=torch.float32, device=dev)
+        nu = torch.zeros(B + 1, dtype=torch.int32, device=dev)  # [B] counts + overflow flag
+        _lib.check(lib.mv_cell_means(_ptr(pred), _ptr(target), _ptr(nuclei), nuclei.element_size(), B, C, H * W, cap, _ptr(mp),
+                                     _ptr(mt), _ptr(ids), _ptr(cnt), _ptr(nu), ctypes.c_void_p(nu.data_ptr() + 4 * B), _stream()),
+                   "mv_cell_means")
+        host = nu.cpu()
+        if int(host[B]) == 0:
+            break
+        cap *= 2  # an image holds more nuclei than rows: retry with a larger table (raises when shared memory runs out)
+    n = int(host[:B].sum())
+    op = torch.empty((n, C), dtype=torch.float32, device=dev)
+    ot = torch.empty((n, C), dtype=torch.float32, device=dev) if target is not None else None
+    oi = torch.empty((n,), dtype=torch.int64, device=dev)
+    oc = torch.empty((n,), dtype=torch.float32, device=dev)
+    if n > 0:
+        _lib.check(lib.mv_cell_means_pack(_ptr(mp), _ptr(mt), _ptr(ids), _ptr(cnt), _ptr(nu), B, C, cap, _ptr(op), _ptr(ot),
+                                          _ptr(oi), _ptr(oc), _stream()), "mv_cell_means_pack")
+    if return_counts:
+        return op, ot, oi, nu[:B], oc
+    return op, ot, oi, nu[:B]
