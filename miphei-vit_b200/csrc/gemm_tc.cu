@@ -761,26 +761,49 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int heads = p.n / 16;
         const float* w2 = reinterpret_cast<const float*>(p.in2);
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
-#pragma unroll 1
-        for (int hl = 0; hl < BLOCK_N / 16; ++hl) {
-          const int hd = n_blk * (BLOCK_N / 16) + hl;
-          if (hd >= heads) break;  // warp-uniform
-          uint32_t v[16];
-          tmem_ld16(taddr + hl * 16, v);
-          tmem_ld_wait();
-          float acc = __ldg(p.resid + hd);
+        // the tile's BLOCK_N / 16 gates of this row are collected in registers and stored as 16-byte vectors (they used to
+        // leave as sixteen 2-byte stores per row, each lane on a different line)
+        constexpr int HPT = BLOCK_N / 16;  // heads per tile
+        float gate[HPT];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int n = hd * 16 + j4 * 4;
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + n));
-            acc += fmaxf(__uint_as_float(v[j4 * 4 + 0]) * sc.x + sh.x, 0.f) * ww.x;
-            acc += fmaxf(__uint_as_float(v[j4 * 4 + 1]) * sc.y + sh.y, 0.f) * ww.y;
-            acc += fmaxf(__uint_as_float(v[j4 * 4 + 2]) * sc.z + sh.z, 0.f) * ww.z;
-            acc += fmaxf(__uint_as_float(v[j4 * 4 + 3]) * sc.w + sh.w, 0.f) * ww.w;
+        for (int hl = 0; hl < HPT; ++hl) {
+          const int hd = n_blk * HPT + hl;
+          gate[hl] = 0.f;
+          if (hd < heads) {  // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(taddr + hl * 16, v);
+            tmem_ld_wait();
+            float acc = __ldg(p.resid + hd);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int n = hd * 16 + j4 * 4;
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + n));
+              acc += fmaxf(__uint_as_float(v[j4 * 4 + 0]) * sc.x + sh.x, 0.f) * ww.x;
+              acc += fmaxf(__uint_as_float(v[j4 * 4 + 1]) * sc.y + sh.y, 0.f) * ww.y;
+              acc += fmaxf(__uint_as_float(v[j4 * 4 + 2]) * sc.z + sh.z, 0.f) * ww.z;
+              acc += fmaxf(__uint_as_float(v[j4 * 4 + 3]) * sc.w + sh.w, 0.f) * ww.w;
+            }
+            gate[hl] = sigmoid_f(acc);
           }
-          if (row_ok) o[hd] = __float2bfloat16(1.f / (1.f + __expf(-acc)));
+        }
+        if (row_ok) {
+          const int h0 = n_blk * HPT;
+          if constexpr (HPT % 8 == 0) {
+            if (p.ldo % 8 == 0 && h0 + HPT <= heads && (reinterpret_cast<uintptr_t>(o + h0) & 15) == 0) {
+#pragma unroll
+              for (int q = 0; q < HPT / 8; ++q) store_bf16x8(o + h0 + 8 * q, gate + 8 * q);
+            } else {
+#pragma unroll
+              for (int hl = 0; hl < HPT; ++hl)
+                if (h0 + hl < heads) o[h0 + hl] = __float2bfloat16(gate[hl]);
+            }
+          } else {
+#pragma unroll
+            for (int hl = 0; hl < HPT; ++hl)
+              if (h0 + hl < heads) o[h0 + hl] = __float2bfloat16(gate[hl]);
+          }
         }
       } else if constexpr (MODE == MV_GEMM_HEAD_CONV) {
         // columns [16*tap, 16*tap+16): t[h] = sum_c W3[h, c, tap] * f[c](pixel + tap); the 3x3 conv acts on f * g_h,
