@@ -20,7 +20,8 @@
 
 namespace mv {
 
-constexpr int ATB_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 softmax-backward math (one row per thread)
+constexpr int ATB_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax-backward math: TWO threads per row
+                                      // (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4), 32 columns each
 constexpr int ATB_RTILE = 128 * 128;   // bytes of one [128 x 64] bf16 row-operand tile
 constexpr int ATB_CTILE = 64 * 128;    // bytes of one [64 x 64] bf16 column-operand tile
 constexpr int ATB_TMEM = 256;          // X 64 | Y 64 | acc1 64 | acc2 64 : two CTAs per SM share the 512 columns
@@ -87,9 +88,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       mbar_init(c_empty(s), 1);
     }
     mbar_init(bar_xy, 1);
-    mbar_init(bar_pd, 128);
+    mbar_init(bar_pd, 256);
     mbar_init(bar_acc, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -166,8 +167,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile; 16 reduction rows = 2 KB per step
-            if (DKV) umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + k * 8, dm2 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
-            umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + k * 8, dm1 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
+            // P / dS of column half h sit packed in the first 16 TMEM columns of that half's own 32-column range
+            const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
+            if (DKV) umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_X + acol, dm2 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
+            umma_bf16_ts(tmem_base + COL_A2, tmem_base + COL_Y + acol, dm1 + so + (2048 >> 4) * k, idesc_acc, (ib | k) != 0);
           }
           umma_commit(c_empty(cs));
           if (ib == ncb - 1) {
@@ -184,8 +187,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
   } else {
     // ===================== softmax-backward math + epilogue (4 warps, thread = row) =====================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;   // which 32 of the 64 tile columns (and of the 64 accumulator columns) this thread owns
     const int r = quad * 32 + lane;
-    const int tid = threadIdx.x - 64;  // 0..127
+    const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n_tok = p.n_tok;
     uint32_t xph = 0, aph = 0;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       // fetched ONE TILE AHEAD into a register, so the global-load latency is not on the per-tile critical path
       auto load_stat = [&](int ib) {
         const int q = ib * 64 + (tid & 63);
-        if (q >= n_tok) return 0.f;
+        if (q >= n_tok || tid >= 128) return 0.f;
         return tid < 64 ? p.lse[vec0 + q] * 1.4426950408889634f : p.dsum[vec0 + q];
       };
       float stat_next = DKV ? load_stat(0) : 0.f;
@@ -213,69 +217,58 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         const float* sd = s_dsum + (itn & 1) * 64;
         if (DKV) {  // double-buffered smem copy of this tile's statistics
           if (tid < 64) s_lse[(itn & 1) * 64 + tid] = stat_next;
-          else s_dsum[(itn & 1) * 64 + tid - 64] = stat_next;
-          nbar(1, 128);
+          else if (tid < 128) s_dsum[(itn & 1) * 64 + tid - 64] = stat_next;
+          nbar(1, 256);
           if (ib + 1 < ncb) stat_next = load_stat(ib + 1);
         }
         mbar_wait(bar_xy, xph);
         tc_fence_after();
-        uint32_t pp[2][16], pd[2][16];
-        uint32_t xs[2][32], ys[2][32];  // one TMEM round trip for the whole 64-column tile row
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          tmem_ld32(trow + COL_X + ci * 32, xs[ci]);
-          tmem_ld32(trow + COL_Y + ci * 32, ys[ci]);
-        }
+        // this thread's 32 columns [32*half, 32*half+32) of X and Y: one TMEM round trip; P / dS (bf16 pairs) go back into
+        // the first 16 columns of the SAME range, so the two threads of a row never touch each other's columns
+        uint32_t x[32], y[32], pp[16], pd[16];
+        tmem_ld32(trow + COL_X + half * 32, x);
+        tmem_ld32(trow + COL_Y + half * 32, y);
         tmem_ld_wait();
         // dS is formed WITHOUT the softmax scale (applied once per item to the accumulator in the epilogue), and tiles
         // that lie completely inside the sequence skip the per-element bounds predicates
         const bool interior = (ob * 128 + 127 < n_tok) && (ib * 64 + 63 < n_tok);  // CTA-uniform
+        if (interior) {
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const uint32_t* x = xs[ci];
-          const uint32_t* y = ys[ci];
-          if (interior) {
+          for (int j = 0; j < 16; ++j) {
+            float pv[2], dv[2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float pv[2], dv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int col = ci * 32 + 2 * j + e;
-                const float l2 = DKV ? sl[col] : lse_r;
-                const float dd = DKV ? sd[col] : dsum_r;
-                const float pr = ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2);
-                pv[e] = pr;
-                dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
-              }
-              pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
-              pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
+            for (int e = 0; e < 2; ++e) {
+              const int col = half * 32 + 2 * j + e;
+              const float l2 = DKV ? sl[col] : lse_r;
+              const float dd = DKV ? sd[col] : dsum_r;
+              const float pr = ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2);
+              pv[e] = pr;
+              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
             }
-          } else {
+            pp[j] = pack_bf16x2(pv[0], pv[1]);
+            pd[j] = pack_bf16x2(dv[0], dv[1]);
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float pv[2], dv[2];
+          for (int j = 0; j < 16; ++j) {
+            float pv[2], dv[2];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int col = ci * 32 + 2 * j + e;
-                const int icol = ib * 64 + col;
-                const bool ok = orow < n_tok && icol < n_tok;
-                const float l2 = DKV ? sl[col] : lse_r;
-                const float dd = DKV ? sd[col] : dsum_r;
-                const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
-                pv[e] = pr;
-                dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
-              }
-              pp[ci][j] = pack_bf16x2(pv[0], pv[1]);
-              pd[ci][j] = pack_bf16x2(dv[0], dv[1]);
+            for (int e = 0; e < 2; ++e) {
+              const int col = half * 32 + 2 * j + e;
+              const int icol = ib * 64 + col;
+              const bool ok = orow < n_tok && icol < n_tok;
+              const float l2 = DKV ? sl[col] : lse_r;
+              const float dd = DKV ? sd[col] : dsum_r;
+              const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
+              pv[e] = pr;
+              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
             }
+            pp[j] = pack_bf16x2(pv[0], pv[1]);
+            pd[j] = pack_bf16x2(dv[0], dv[1]);
           }
         }
-        // every column of this row has been read (this warp is the only reader of its lanes): P / dS overwrite X / Y
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          if (DKV) tmem_st16(trow + COL_X + ci * 16, pp[ci]);
-          tmem_st16(trow + COL_Y + ci * 16, pd[ci]);
-        }
+        if (DKV) tmem_st16(trow + COL_X + half * 32, pp);
+        tmem_st16(trow + COL_Y + half * 32, pd);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_pd);
@@ -284,40 +277,30 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       // ---- epilogue: accumulators -> bf16 rows of dqkv
       mbar_wait(bar_acc, aph);
       tc_fence_after();
-      uint32_t a0[32], a1[32], b0[32], b1[32];
-      tmem_ld32(trow + COL_A2, a0);
-      tmem_ld32(trow + COL_A2 + 32, a1);
-      if (DKV) {
-        tmem_ld32(trow + COL_A1, b0);
-        tmem_ld32(trow + COL_A1 + 32, b1);
-      }
+      uint32_t a0[32], b0[32];
+      tmem_ld32(trow + COL_A2 + half * 32, a0);
+      if (DKV) tmem_ld32(trow + COL_A1 + half * 32, b0);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty);
       if (orow < n_tok) {
-        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + h * 64;
-        auto store64 = [&](__nv_bfloat16* dst, const uint32_t* lo, const uint32_t* hi, float mul) {
+        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + h * 64 + half * 32;
+        auto store32 = [&](__nv_bfloat16* dst, const uint32_t* v, float mul) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(lo[8 * j + 0]) * mul, __uint_as_float(lo[8 * j + 1]) * mul);
-            u.y = pack_bf16x2(__uint_as_float(lo[8 * j + 2]) * mul, __uint_as_float(lo[8 * j + 3]) * mul);
-            u.z = pack_bf16x2(__uint_as_float(lo[8 * j + 4]) * mul, __uint_as_float(lo[8 * j + 5]) * mul);
-            u.w = pack_bf16x2(__uint_as_float(lo[8 * j + 6]) * mul, __uint_as_float(lo[8 * j + 7]) * mul);
+            u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
             reinterpret_cast<uint4*>(dst)[j] = u;
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(hi[8 * j + 0]) * mul, __uint_as_float(hi[8 * j + 1]) * mul);
-            w.y = pack_bf16x2(__uint_as_float(hi[8 * j + 2]) * mul, __uint_as_float(hi[8 * j + 3]) * mul);
-            w.z = pack_bf16x2(__uint_as_float(hi[8 * j + 4]) * mul, __uint_as_float(hi[8 * j + 5]) * mul);
-            w.w = pack_bf16x2(__uint_as_float(hi[8 * j + 6]) * mul, __uint_as_float(hi[8 * j + 7]) * mul);
-            reinterpret_cast<uint4*>(dst)[4 + j] = w;
           }
         };
         if (DKV) {
-          store64(base + p.dim, a0, a1, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
-          store64(base + 2 * p.dim, b0, b1, 1.f);  // dV = P^T dO                        (acc1)
+          store32(base + p.dim, a0, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
+          store32(base + 2 * p.dim, b0, 1.f);  // dV = P^T dO                        (acc1)
         } else {
-          store64(base, a0, a1, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
+          store32(base, a0, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
         }
       }
       aph ^= 1;
