@@ -110,6 +110,8 @@ typedef struct mv_gemm_args {
   int32_t reserved2;
   float* colstats;    /* LINEAR + bf16 out: fp32 [2, N] += per-column (sum, sum of squares) of the stored values —
                          BatchNorm batch statistics of a train-mode conv; out may be NULL (statistics only) */
+  int32_t kskip_begin, kskip_end; /* LINEAR: K range [begin, end) (multiples of 64) whose B columns are all zero and is
+                                     not loaded at all (dT = [dQ | dK | dV] . [aB_q ; 0 ; aB_v]^T skips the dK third) */
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);

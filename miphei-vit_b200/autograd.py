@@ -99,7 +99,7 @@ def encoder_forward_train(eng, x, tape):
     return ws.fmap
 
 
-def encoder_backward(eng, tape, dmap, on_start=None):
+def encoder_backward(eng, tape, dmap, on_start=None, sink=False):
     """dmap: NHWC bf16 gradient of the resized feature map. Returns per-block (dA_q, dB_q, dA_v, dB_v)."""
     B, N, D = tape.B, eng.N, eng.D
     if on_start is not None:
@@ -118,10 +118,14 @@ def encoder_backward(eng, tape, dmap, on_start=None):
         ops.layernorm_bwd(tape.xmid[i], pb["n2w"], tape.dxn, dres=dx, out=tape.dx[nxt], out_bf16=tape.dxb[nxt])
         ops.gemm(tape.dxb[nxt], pb["wproj_bwd"], out=tape.do)
         ops.attn_bwd(tape.qkv[i], tape.o[i], tape.do, tape.lse[i], B, N, eng.heads, dqkv=dq, dsum=tape.dsum)
-        ops.gemm(dq[:, :3 * D], pb["bcat"], out=dq[:, 3 * D:3 * D + 16])
+        # dT = [dQ | dK | dV] . [alpha B_q ; 0 ; alpha B_v]^T: the dK third multiplies zeros and is never loaded
+        ops.gemm(dq[:, :3 * D], pb["bcat"], out=dq[:, 3 * D:3 * D + 16], kskip=(D, 2 * D))
         lq, lv = pb["lora"]
-        gAq, gBq = torch.empty_like(lq.A), torch.empty_like(lq.B)
-        gAv, gBv = torch.empty_like(lv.A), torch.empty_like(lv.B)
+        if sink:  # trainer mode: the kernels write straight into the flat gradient buffer (p.grad are views of it)
+            gAq, gBq, gAv, gBv = lq.A.grad, lq.B.grad, lv.A.grad, lv.B.grad
+        else:
+            gAq, gBq = torch.empty_like(lq.A), torch.empty_like(lq.B)
+            gAv, gBv = torch.empty_like(lv.A), torch.empty_like(lv.B)
         ops.lora_grads(tape.xn_ext[i], dq, D, lq.alpha, gAq, gAv, gBq, gBv, workspace=tape.lora_ws)
         grads[i] = (gAq, gBq, gAv, gBv)
         if i > 0:
@@ -153,14 +157,17 @@ class _MipheiFn(torch.autograd.Function):
             for p, g in grads.items():
                 p.grad.copy_(g)
             grads = {}
-        lgrads = encoder_backward(eng, tape, dfmap, on_start=eng.on_encoder_backward_start)
-        for pb, (gAq, gBq, gAv, gBv) in zip(eng.blocks, lgrads):
-            lq, lv = pb["lora"]
-            for p, g in ((lq.A, gAq), (lq.B, gBq), (lv.A, gAv), (lv.B, gBv)):
-                if sink:
-                    p.grad.copy_(g)
-                else:
-                    grads[p] = g
+        sink_lora = sink and all(q.grad is not None and q.grad.is_contiguous() for pb in eng.blocks[:1] for l in pb["lora"]
+                                 for q in (l.A, l.B))
+        lgrads = encoder_backward(eng, tape, dfmap, on_start=eng.on_encoder_backward_start, sink=sink_lora)
+        if not sink_lora:
+            for pb, (gAq, gBq, gAv, gBv) in zip(eng.blocks, lgrads):
+                lq, lv = pb["lora"]
+                for p, g in ((lq.A, gAq), (lq.B, gBq), (lv.A, gAv), (lv.B, gBv)):
+                    if sink:
+                        p.grad.copy_(g)
+                    else:
+                        grads[p] = g
         return (None, None) + tuple(grads.get(p) for p in params)
 
 

@@ -65,6 +65,7 @@ struct GemmDev {
   //   accumulator   [3] epilogue warp 2 waiting for an accumulator   [4] epilogue warp 2 busy   [5] CTA lifetime
   //   [6] tiles of this CTA
   long long* prof;
+  int kskip0, kskip1;  // k blocks [kskip0, kskip1) are skipped (their B columns are zero)
 };
 
 // PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
@@ -309,6 +310,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           w_px = prem - w_py * p.conv_w;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kb >= p.kskip0 && kb < p.kskip1) continue;
           const long long t0_ = (kProf && p.prof) ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (kProf && p.prof) prof_acc[0] += clock64() - t0_;
@@ -396,6 +398,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kb >= p.kskip0 && kb < p.kskip1) continue;
           t0_ = (kProf && p.prof) ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
           if (kProf && p.prof) prof_acc[1] += clock64() - t0_;
@@ -1012,6 +1015,8 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.splits = 1;
   p.colstats = a.colstats;
   p.prof = g_gemm_prof;
+  p.kskip0 = a.kskip_begin / GEMM_BLOCK_K;
+  p.kskip1 = a.kskip_end / GEMM_BLOCK_K;
   if (MODE == MV_GEMM_NN_ATOMIC) {
     const int sms = device_sms() > 0 ? device_sms() : 148;
     const int mn = p.num_m_blocks * p.num_n_blocks;
@@ -1087,6 +1092,9 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   MV_CHECK_ARG(!a.aux || ((reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && a.ldaux % 8 == 0), "mv_gemm_bf16: aux alignment");
   MV_CHECK_ARG(!a.scale || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0, "mv_gemm_bf16: scale alignment");
   MV_CHECK_ARG(!a.shift || (reinterpret_cast<uintptr_t>(a.shift) & 15) == 0, "mv_gemm_bf16: shift alignment");
+  MV_CHECK_ARG(a.kskip_end == 0 || (a.mode == MV_GEMM_LINEAR && !a.conv && a.kskip_begin > 0 && a.kskip_begin % 64 == 0 &&
+                                    a.kskip_end % 64 == 0 && a.kskip_end > a.kskip_begin && a.kskip_end <= a.k),
+               "mv_gemm_bf16: kskip must be a non-empty 64-aligned K range after the first k block, LINEAR mode only");
 
   // CTA pairs (cta_group::2) for the big plain GEMMs; reserved2: 0 = auto, 1 = never, 2 = always (when legal)
   static const int pair_env = [] { const char* e = getenv("MV_GEMM_PAIR"); return e ? atoi(e) : -1; }();  // 0 disables

@@ -37,6 +37,7 @@ class GemmArgs(ctypes.Structure):
         ("conv_c0", c_i32), ("conv_c1", c_i32),
         ("reserved_splits", c_i32), ("reserved2", c_i32),
         ("colstats", c_void_p),
+        ("kskip_begin", c_i32), ("kskip_end", c_i32),
     ]
 
 

@@ -32,7 +32,8 @@ def _rowmajor(t, name):
 
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
-         resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False, pair=0):
+         resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False, pair=0,
+         kskip=None):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
     lib = _lib_for(a)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -123,6 +124,8 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     args.resid_row_mod = 1 if resid_row_mod else 0
     args.block_n = block_n
     args.reserved2 = pair  # 0 auto, 1 never, 2 always: CTA-pair (cta_group::2) tiles
+    if kskip is not None:  # K range with all-zero B columns: never loaded
+        args.kskip_begin, args.kskip_end = int(kskip[0]), int(kskip[1])
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")
     return out
 
