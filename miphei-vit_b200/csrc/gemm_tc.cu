@@ -527,6 +527,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       if constexpr (MODE == MV_GEMM_SWIGLU_BWD) load_h(egrp, hgn, hvn);
+      // GATE_MASK (heads backward, 128-wide two-CTA-per-SM tiles): the per-(row, head) gate gradients of the WHOLE tile are
+      // fetched before the accumulator wait — this epilogue-bound kernel otherwise exposes their latency once per chunk
+      constexpr bool kPreloadDu = MODE == MV_GEMM_LINEAR && LIGHT && BLOCK_N == 128;
+      float du_tile[kPreloadDu ? 4 : 1][4];
+      if constexpr (kPreloadDu) {
+        if (p.act == MV_ACT_GATE_MASK) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int nnm = n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int mm = m_blk * GEMM_BLOCK_M + quad * 32 + it * 8 + (lane >> 2);
+              du_tile[c][it] = 0.f;
+              if (mm < p.m && nnm < p.n)
+                du_tile[c][it] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nnm >> 4)]);
+            }
+          }
+        }
+      }
       const long long te0_ = (kProf && p.prof) ? clock64() : 0;
       mbar_wait(tfull_bar(as), aphase);
       const long long te1_ = (kProf && p.prof) ? clock64() : 0;
@@ -546,7 +565,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int c = egrp; c < NC; c += EGRPS) {
           // GATE_MASK: the per-(row, head) gate gradients of this chunk, fetched before the TMEM wait (hidden latency)
           float du4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.act == MV_ACT_GATE_MASK) {
+          if constexpr (kPreloadDu) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc == c) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) du4[it] = du_tile[cc][it];
+              }
+          } else if (p.act == MV_ACT_GATE_MASK) {
             const int nnm = n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -864,7 +890,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (j < p.n) {
             const float z = acc[j] + __ldg(p.shift + j);
             const float e = __expf(2.f * z);
-            const float t = 1.f - 2.f / (e + 1.f);  // tanh
+            const float t = 1.f - __fdividef(2.f, e + 1.f);  // tanh (fast divide: 2 ulp, e + 1 >= 1)
             const long long oi = ((long long)bimg * p.n + j) * hw + rem;  // NCHW
             if (p.out_f32 == 1) reinterpret_cast<float*>(p.out)[oi] = t;
             else if (p.out_f32 == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[oi] = __float2bfloat16(t);
