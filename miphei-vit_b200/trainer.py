@@ -133,39 +133,6 @@ class Trainer:
         return loss
 
 
-def smoke_step(model, cfg, sd, x_cpu):
-    """One training step on the small smoke model, gradients checked against the oracle (called by smoke())."""
-    from oracle import model as om
-
-    y = om.synthetic_targets(x_cpu.shape[0], cfg.out_chans, cfg.img_size, seed=321)
-    w = torch.linspace(1.0, 4.0, cfg.out_chans)
-    sd = {k: v.clone() for k, v in sd.items()}
-    keys = om.trainable_keys(sd)
-    for k in keys:
-        sd[k].requires_grad_(True)
-    pred = om.miphei_forward(sd, x_cpu, cfg, training=True)
-    loss_ref = om.weighted_mse_loss(y, pred, w, 50.0)
-    gref = dict(zip(keys, torch.autograd.grad(loss_ref, [sd[k] for k in keys])))
-    tr = Trainer(model, marker_weights=w, batch_size=x_cpu.shape[0], total_steps=100, warmup_steps=2)
-    tr.gflat.zero_()
-    model.train()
-    out = model(x_cpu.cuda())
-    loss, dpred = ops.loss_fwd_bwd(out.detach().float().contiguous(), y.cuda(), tr.marker_weights, lambda_factor=50.0)
-    out.backward(dpred.to(out.dtype))
-    got = {n: p.grad.detach().float().cpu() for n, p in tr.order}
-    a = torch.cat([got[k].flatten() for k in keys])
-    b = torch.cat([gref[k].flatten() for k in keys])
-    cos = om.cosine(a, b)
-    lora = [k for k in keys if ".lora_" in k]
-    cos_lora = om.cosine(torch.cat([got[k].flatten() for k in lora]), torch.cat([gref[k].flatten() for k in lora]))
-    print("smoke: train loss %.5f (oracle %.5f), gradient cosine all %.6f, LoRA %.6f" % (
-        loss.item(), loss_ref.item(), cos, cos_lora))
-    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
-    assert cos >= 0.999 and cos_lora >= 0.995, (cos, cos_lora)
-    l2 = tr.step(x_cpu.cuda(), y.cuda())
-    assert torch.isfinite(l2).all()
-
-
 def bench_train(model, args, rank, world, dev):
     """BASELINE configs[2]: training step (fwd + bwd + loss + clip + Adam), batch 32 per GPU, weak scaling."""
     if getattr(args, "no_train", False):

@@ -1,6 +1,6 @@
 """Isolates the decoder: hand-written train fwd/bwd vs torch fp32 autograd on identical inputs and weights."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import model as om
 from miphei_vit_b200 import ops
 from miphei_vit_b200.generators.mipheivit import get_vitmatte

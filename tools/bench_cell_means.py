@@ -2,12 +2,26 @@
 loop on the same GPU (restated here with torch ops — the reference function itself is not importable on the GPU box)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 from miphei_vit_b200 import ops
-from oracle import cell_means as oc
+
+
+def synthetic_nuclei(batch, size, n_cells, seed=0):
+    """Label maps with `n_cells` random discs per image (later discs overwrite earlier ones)."""
+    g = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size]
+    out = np.zeros((batch, size, size), dtype=np.int64)
+    for b in range(batch):
+        for k in range(n_cells):
+            cy, cx, r = g.integers(0, size), g.integers(0, size), g.integers(2, 9)
+            out[b][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 1 + 7 * k + 1000003 * b
+    return torch.from_numpy(out)
+
+
 B, C, S = 32, 16, 256
 pred = torch.rand(B, C, S, S, device="cuda")
 target = torch.rand(B, C, S, S, device="cuda")
-nuclei = oc.synthetic_nuclei(B, S, 250, seed=1).cuda()
+nuclei = synthetic_nuclei(B, S, 250, seed=1).cuda()
 def torch_loop():
     outs = []
     for b in range(B):
