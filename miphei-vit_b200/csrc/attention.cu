@@ -13,7 +13,8 @@
 // so the tensor core works for one slot while the other slot's warpgroup does its exponentials:
 //   warp 0 (1 thread) : TMA producer — Q (2 buffers / slot) and K|V blocks (2 stages / slot), 128-byte swizzle
 //   warp 1 (1 thread) : tcgen05.mma issuer — S = Q K_j^T (SS), O += P V_j (A = P from TMEM, V MN-major from smem)
-//   warps 2..5 / 6..9 : softmax warpgroup of slot A / B, one query row per thread: running max with LAZY rescale of the
+//   warps 2..9 / 10..17: softmax warps of slot A / B, TWO threads per query row (same TMEM lane quadrant, the key block's
+//                       columns split between them; row max / row sum exchanged through shared memory): running max with LAZY rescale of the
 //                       O accumulator (only when the max grows by > 2^8), p = exp2(s*c - m), bf16 P written over S in
 //                       TMEM, final O / l -> global.
 // TMEM per slot: S/P at +0 (kb fp32 columns, P aliases the first kb/2), O at +128 (64 columns); slots at 0 and 256.
@@ -22,7 +23,7 @@
 
 namespace mv {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;  // TMA warp, MMA warp, 2 slots x 8 softmax warps (two threads per query row)
 constexpr int ATT_QBYTES = 128 * 128;       // one [128 x 64] bf16 tile
 constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // log2 units
 
@@ -62,6 +63,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   auto bar = [&](int slot, int idx) { return bar_base + 8u * (slot * 11 + idx); };
   const uint32_t tmem_slot = bar_base + 8u * 22;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 22);
+  // row max (double buffered by key-block parity) and row sum exchanged between the two threads of a row:
+  // xchg[slot][buffer 0,1 = max, 2 = sum][column half][128 rows]
+  float* xchg = reinterpret_cast<float*>(smem_gen + misc_off + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     for (int s = 0; s < 2; ++s) {
       for (int i = 0; i < 8; ++i) mbar_init(bar(s, i), 1);
       mbar_init(bar(s, 8), 1);    // s_full
-      mbar_init(bar(s, 9), 128);  // p_full
+      mbar_init(bar(s, 9), 256);  // p_full
       mbar_init(bar(s, 10), 1);   // o_full
     }
     fence_barrier_init();
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kb);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       const int ksteps = p.kb / 16;
+      const int csplit_m = (p.kb / 32 + 1) >> 1;
       auto issue_s = [&](int s, int g) {
         const int it = g / nb, j = g - it * nb;
         const int qb = it & 1, st = g & 1;
@@ -151,7 +156,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         const uint32_t a = tmem_base + s * 256;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t dv = umma_desc_sw128(sV(s, st) + k * 2048, 1024, 1024);
-          umma_bf16_ts(d, a + k * 8, dv, idesc_pv, (j | k) != 0);
+          // P (bf16 pairs, 8 TMEM columns per 16 keys): keys of the first csplit 32-key chunks start at column 0, the
+          // rest (written by the row's second softmax thread) at column 32 csplit
+          const uint32_t pcol = k < 2 * csplit_m ? k * 8 : 32 * csplit_m + (k - 2 * csplit_m) * 8;
+          umma_bf16_ts(d, a + pcol, dv, idesc_pv, (j | k) != 0);
         }
         umma_commit(bar(s, 6 + st));  // K|V stage free
         if (j == nb - 1) umma_commit(bar(s, 10));
@@ -169,30 +177,37 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       }
     }
   } else {
-    // ===================== softmax warpgroups =====================
-    const int s = (warp - 2) >> 2;   // slot
-    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
+    // ===================== softmax warps =====================
+    const int s = (warp - 2) >> 3;         // slot
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = ((warp - 2) & 7) >> 2;  // which part of the key block's columns / of the 64 output dims
+    const int r = quad * 32 + lane;        // query row within the tile == TMEM lane
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + s * 256;
     const int n_tok = p.n_tok, kb = p.kb;
     const int full32 = kb / 32;
     const bool tail16 = (kb & 31) != 0;
+    // 32-column chunks [cbeg, cend) of the key block belong to this thread; the 16-column tail goes to half 1
+    const int csplit = (full32 + 1) >> 1;
+    const int cbeg = half ? csplit : 0, cend = half ? full32 : csplit;
+    const bool my_tail = tail16 && half == 1;
     const float c = p.scale_log2e;
+    float* xs = xchg + s * (3 * 2 * 128);
+    auto slot_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); };
     int g = 0;
     for (int it = 0; it < n_items[s]; ++it) {
       const int t = t0 + s + 2 * it;
       const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
       const int b = bh / p.heads, h = bh - b * p.heads;
-      float m_ref = -INFINITY, l = 0.f;
+      float m_ref = -INFINITY, l = 0.f;  // l: this thread's share of the row sum
       for (int j = 0; j < nb; ++j, ++g) {
         mbar_wait(bar(s, 8), g & 1);
         tc_fence_after();
         const int key0 = j * kb;
         const bool partial = key0 + kb > n_tok;  // block holds keys beyond the sequence: mask them
-        // ---- pass 1: block row max
+        // ---- pass 1: row max over this thread's columns
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int cc = 0; cc < full32; ++cc) {
+        for (int cc = cbeg; cc < cend; ++cc) {
           uint32_t v[32];
           tmem_ld32(trow + cc * 32, v);
           tmem_ld_wait();
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
               if (key0 + cc * 32 + q < n_tok) mx = fmaxf(mx, __uint_as_float(v[q]));
           }
         }
-        if (tail16) {
+        if (my_tail) {
           uint32_t v[16];
           tmem_ld16(trow + full32 * 32, v);
           tmem_ld_wait();
@@ -213,34 +228,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
           for (int q = 0; q < 16; ++q)
             if (key0 + full32 * 32 + q < n_tok) mx = fmaxf(mx, __uint_as_float(v[q]));
         }
+        // exchange with the row's other thread (buffer = block parity: the partner may already be one block ahead)
+        float* xm = xs + (g & 1) * 256;
+        xm[half * 128 + r] = mx;
+        slot_bar();
+        mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
         const float m_new = fmaxf(m_ref, mx * c);
-        // ---- lazy rescale of the accumulator (warp-uniform decision: tcgen05.ld/st are warp collectives)
+        // ---- lazy rescale of the accumulator (warp-uniform decision: tcgen05.ld/st are warp collectives; both warps of
+        // a quadrant see the same 32 rows, so they take the same branch); each thread rescales its 32 of the 64 O columns
         const bool grow = (j == 0) || (m_new - m_ref > ATT_RESCALE_THRESHOLD);
         if (__any_sync(0xffffffffu, grow)) {
           const float m_use = grow ? m_new : m_ref;
           if (j > 0) {
             const float alpha = grow ? ex2_approx(m_ref - m_new) : 1.f;
             l *= alpha;
-            uint32_t o0[32], o1[32];
-            tmem_ld32(trow + 128, o0);
-            tmem_ld32(trow + 160, o1);
+            uint32_t o[32];
+            tmem_ld32(trow + 128 + half * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              o0[q] = __float_as_uint(__uint_as_float(o0[q]) * alpha);
-              o1[q] = __float_as_uint(__uint_as_float(o1[q]) * alpha);
-            }
-            tmem_st16(trow + 128, reinterpret_cast<uint32_t(&)[16]>(o0[0]));
-            tmem_st16(trow + 144, reinterpret_cast<uint32_t(&)[16]>(o0[16]));
-            tmem_st16(trow + 160, reinterpret_cast<uint32_t(&)[16]>(o1[0]));
-            tmem_st16(trow + 176, reinterpret_cast<uint32_t(&)[16]>(o1[16]));
+            for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+            tmem_st16(trow + 128 + half * 32, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+            tmem_st16(trow + 144 + half * 32, reinterpret_cast<uint32_t(&)[16]>(o[16]));
           }
           m_ref = m_use;
         }
         // ---- pass 2: p = exp2(s*c - m_ref) -> bf16, written over S
         float sum = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < full32; ++cc) {
+        for (int cc = cbeg; cc < cend; ++cc) {
           uint32_t v[32], pk[16];
           tmem_ld32(trow + cc * 32, v);
           tmem_ld_wait();
@@ -255,9 +270,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             sum += e0 + e1;
             pk[q] = pack_bf16x2(e0, e1);
           }
-          tmem_st16(trow + cc * 16, pk);
+          // P of chunk cc goes to the start of THIS thread's own S column range (half 0: 16 cc, half 1: 32 csplit +
+          // 16 (cc - csplit)) — always columns this thread has already read, never the partner's unread scores
+          tmem_st16(trow + (half ? 32 * csplit + 16 * (cc - csplit) : 16 * cc), pk);
         }
-        if (tail16) {
+        if (my_tail) {
           uint32_t v[16], pk[16];
           tmem_ld16(trow + full32 * 32, v);
           tmem_ld_wait();
@@ -271,44 +288,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
           }
 #pragma unroll
           for (int q = 8; q < 16; ++q) pk[q] = 0u;
-          tmem_st16(trow + full32 * 16, pk);  // upper 8 columns land beyond kb/2, inside the dead part of S
+          tmem_st16(trow + 32 * csplit + 16 * (full32 - csplit), pk);  // upper 8 columns: dead (already read) part of S
         }
         l += sum;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar(s, 9));
       }
-      // ---- epilogue of the item: O / l -> bf16 rows
+      // ---- epilogue of the item: O / l -> bf16 rows; row sum = both threads' shares
+      float* xl = xs + 2 * 256;
+      xl[half * 128 + r] = l;
+      slot_bar();
+      const float l_row = l + xl[(half ^ 1) * 128 + r];
       mbar_wait(bar(s, 10), it & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(trow + 128, o0);
-      tmem_ld32(trow + 160, o1);
+      uint32_t o[32];
+      tmem_ld32(trow + 128 + half * 32, o);
       tmem_ld_wait();
       const int q = qt * 128 + r;
       if (q < n_tok) {
-        const float inv = 1.f / l;
-        __nv_bfloat16* orow = p.out + (long long)(b * n_tok + q) * p.ldo + h * 64;
+        const float inv = 1.f / l_row;
+        __nv_bfloat16* orow = p.out + (long long)(b * n_tok + q) * p.ldo + h * 64 + half * 32;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o0[8 * jj + 0]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv);
+          u.x = pack_bf16x2(__uint_as_float(o[8 * jj + 0]) * inv, __uint_as_float(o[8 * jj + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * jj + 2]) * inv, __uint_as_float(o[8 * jj + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * jj + 4]) * inv, __uint_as_float(o[8 * jj + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * jj + 6]) * inv, __uint_as_float(o[8 * jj + 7]) * inv);
           reinterpret_cast<uint4*>(orow)[jj] = u;
         }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o1[8 * jj + 0]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[4 + jj] = u;
-        }
-        if (p.lse) p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l)) * 0.6931471805599453f;
+        if (p.lse && half == 0) p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l_row)) * 0.6931471805599453f;
       }
+      slot_bar();  // the sum buffer is reused by the next item
     }
   }
   tc_fence_before();
@@ -341,7 +353,7 @@ extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
-  const int smem = 12 * ATT_QBYTES + 8 * 24 + 1024;
+  const int smem = 12 * ATT_QBYTES + 256 + 2 * 3 * 2 * 128 * 4 + 1024;  // tiles, barriers, row-statistic exchange
   const uint64_t rows = (uint64_t)batch * n_tok;
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
   const CUtensorMap* tkv = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, p.kb);
