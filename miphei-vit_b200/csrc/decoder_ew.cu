@@ -121,39 +121,62 @@ __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long
   }
 }
 
-// NHWC bf16 [B,h,w,C] -> [B,2h,2w,C], bilinear, align_corners = False; one thread per (output pixel, 8 channels)
+// NHWC bf16 [B,h,w,C] -> [B,2h,2w,C], bilinear, align_corners = False (Fusion_Block, mipheivit.py:88-93).
+// One thread per (INPUT pixel, 8 channels) writes the 2x2 output block it centres: with clamped neighbours m = max(i-1, 0),
+// p = min(i+1, n-1) the exact x2 weights are  out(2i) = 0.25 in(m) + 0.75 in(i),  out(2i+1) = 0.75 in(i) + 0.25 in(p)  in both
+// directions (separable) — 9 sixteen-byte loads and one index decode per 4 outputs instead of 16 loads and 4 decodes.
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h,
                                   int w, int C) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const int cg = C / 8;
-  const long long total = (long long)B * 4 * h * w * cg;
+  const long long total = (long long)B * h * w * cg;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % cg);
   long long r = i / cg;
-  const int ox = (int)(r % (2 * w));
-  r /= (2 * w);
-  const int oy = (int)(r % (2 * h));
-  const long long b = r / (2 * h);
-  const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float ly = sy - y0, lx = sx - x0;
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int x = (int)(r % w);
+  r /= w;
+  const int y = (int)(r % h);
+  const long long b = r / h;
+  const int ym = max(y - 1, 0), yp = min(y + 1, h - 1), xm = max(x - 1, 0), xp = min(x + 1, w - 1);
   const __nv_bfloat16* ib = in + b * (long long)h * w * C + c8 * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(ib + ((long long)y0 * w + x0) * C);
-  const uint4 bq = *reinterpret_cast<const uint4*>(ib + ((long long)y0 * w + x1) * C);
-  const uint4 c = *reinterpret_cast<const uint4*>(ib + ((long long)y1 * w + x0) * C);
-  const uint4 d = *reinterpret_cast<const uint4*>(ib + ((long long)y1 * w + x1) * C);
-  const uint32_t* pa = &a.x; const uint32_t* pb = &bq.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
-  uint32_t o[4];
+  const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
+  float v[3][3][8];  // [row][col][channel]
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 fa = unpack_bf16x2(pa[j]), fb = unpack_bf16x2(pb[j]), fc = unpack_bf16x2(pc[j]), fd = unpack_bf16x2(pd[j]);
-    o[j] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                       w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const uint4 u = *reinterpret_cast<const uint4*>(ib + ((long long)ys[a] * w + xs[q]) * C);
+      const uint32_t* pu = &u.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(pu[j]);
+        v[a][q][2 * j] = f.x;
+        v[a][q][2 * j + 1] = f.y;
+      }
+    }
+  __nv_bfloat16* ob = out + (b * 4 * h * w + (long long)(2 * y) * (2 * w) + 2 * x) * C + c8 * 8;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    float t[3][8];  // rows combined: 3 columns x 8 channels
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        t[q][j] = dy == 0 ? 0.25f * v[0][q][j] + 0.75f * v[1][q][j] : 0.75f * v[1][q][j] + 0.25f * v[2][q][j];
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = dx == 0 ? 0.25f * t[0][j] + 0.75f * t[1][j] : 0.75f * t[1][j] + 0.25f * t[2][j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(ob + ((long long)dy * (2 * w) + dx) * C) = u;
+    }
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // Adjoint of tokens_to_map_kernel: d_tok[b, prefix + gy*g + gx, :] = sum_{oy,ox} Wy[oy,gy] Wx[ox,gx] d_map[b,oy,ox,:];
@@ -315,7 +338,7 @@ extern "C" int mv_upsample2x(const void* in, void* out, int batch, int h, int w,
   using namespace mv;
   MV_CHECK_ARG(in && out && batch > 0 && h > 0 && w > 0 && c % 8 == 0, "mv_upsample2x: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const long long total = (long long)batch * 4 * h * w * (c / 8);
+  const long long total = (long long)batch * h * w * (c / 8);
   MV_LAUNCH(upsample2x_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
   MV_CHECK_LAUNCH("upsample2x");
