@@ -64,27 +64,30 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dup, lon
   r /= w;
   const int y = (int)(r % h);
   const long long b = r / h;
+  // adjoint of the x2 bilinear weights (out(2i) = .25 in(i-1) + .75 in(i), out(2i+1) = .75 in(i) + .25 in(i+1), neighbours
+  // clamped): input i gathers outputs 2i-1 .. 2i+2 with weights (.25, .75, .75, .25); at the borders the clamped
+  // neighbour folds its .25 into the .75 and the out-of-range taps vanish. Separable: 4 x 4 taps, no weight search.
+  const float wy[4] = {y >= 1 ? 0.25f : 0.f, y == 0 ? 1.f : 0.75f, y == h - 1 ? 1.f : 0.75f, y <= h - 2 ? 0.25f : 0.f};
+  const float wx[4] = {x >= 1 ? 0.25f : 0.f, x == 0 ? 1.f : 0.75f, x == w - 1 ? 1.f : 0.75f, x <= w - 2 ? 0.25f : 0.f};
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int oy = max(2 * y - 2, 0); oy <= min(2 * y + 2, 2 * h - 1); ++oy) {
-    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
-    const float ly = sy - y0;
-    const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
-    if (wy == 0.f) continue;
-    for (int ox = max(2 * x - 2, 0); ox <= min(2 * x + 2, 2 * w - 1); ++ox) {
-      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-      const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
-      const float lx = sx - x0;
-      const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-      if (wx == 0.f) continue;
-      const float wgt = wy * wx;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int oy = min(max(2 * y - 1 + a, 0), 2 * h - 1);  // clamped rows / columns carry weight 0
+    float row[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) row[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ox = min(max(2 * x - 1 + q, 0), 2 * w - 1);
       const uint4 u = *reinterpret_cast<const uint4*>(dup + ((b * 2 * h + oy) * 2 * w + ox) * ldu + c8 * 8);
       const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
-      acc[0] += wgt * p0.x; acc[1] += wgt * p0.y; acc[2] += wgt * p1.x; acc[3] += wgt * p1.y;
-      acc[4] += wgt * p2.x; acc[5] += wgt * p2.y; acc[6] += wgt * p3.x; acc[7] += wgt * p3.y;
+      row[0] += wx[q] * p0.x; row[1] += wx[q] * p0.y; row[2] += wx[q] * p1.x; row[3] += wx[q] * p1.y;
+      row[4] += wx[q] * p2.x; row[5] += wx[q] * p2.y; row[6] += wx[q] * p3.x; row[7] += wx[q] * p3.y;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += wy[a] * row[j];
   }
   uint4 o;
   o.x = pack_bf16x2(acc[0], acc[1]);
