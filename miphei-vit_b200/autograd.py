@@ -154,8 +154,11 @@ class _MipheiFn(torch.autograd.Function):
         grads, dfmap = eng.decoder_train.backward(dpred.float())
         sink = eng.direct_grad_sink  # trainer mode: write straight into the flat gradient buffer
         if sink:
-            for p, g in grads.items():
-                p.grad.copy_(g)
+            # ~150 decoder gradients -> their views of the flat gradient buffer in one multi-tensor copy
+            dst = [p.grad for p in grads]
+            src = [g.reshape(p.grad.shape) if g.shape != p.grad.shape else g for p, g in grads.items()]
+            src = [g if g.dtype == d.dtype else g.to(d.dtype) for g, d in zip(src, dst)]
+            torch._foreach_copy_(dst, src)
             grads = {}
         sink_lora = sink and all(q.grad is not None and q.grad.is_contiguous() for pb in eng.blocks[:1] for l in pb["lora"]
                                  for q in (l.A, l.B))

@@ -91,8 +91,12 @@ extern "C" int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_e
   a.a = dtT; a.lda = ldt; a.b = xn_ext; a.ldb = ldx; a.n = d; a.out = g_a; a.ldo = d;
   int rc = mv_gemm_bf16(&a, stream_);
   if (rc) return rc;
-  // dBcat [16, 3D] = T^T [16, M] . dQKV [M, 3D]
-  a.a = tT; a.b = dqkv_ext; a.ldb = ldq; a.n = 3 * d; a.out = g_b; a.ldo = 3 * d;
+  // dBcat [16, 3D] = T^T [16, M] . dQKV [M, 3D]: only the q and v column thirds are used (B_k does not exist), so the
+  // dK third of dQKV is never streamed
+  a.a = tT; a.b = dqkv_ext; a.ldb = ldq; a.n = d; a.out = g_b; a.ldo = 3 * d;
+  rc = mv_gemm_bf16(&a, stream_);
+  if (rc) return rc;
+  a.b = qe + 2ll * d; a.out = g_b + 2ll * d;
   rc = mv_gemm_bf16(&a, stream_);
   if (rc) return rc;
   MV_LAUNCH(lora_unpack_kernel, (8 * d + 255) / 256, 256, 0, stream, g_a, g_b, dA_q, dA_v, dB_q, dB_v, d, alpha);
