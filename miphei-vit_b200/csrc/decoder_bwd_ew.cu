@@ -141,36 +141,42 @@ __global__ void __launch_bounds__(256) heads_ds_kernel(const float* __restrict__
                                                        __nv_bfloat16* __restrict__ ds, float* __restrict__ dbias, int heads,
                                                        int hw) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
-  __shared__ float sh[8];
+  __shared__ float sh[8][16];
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const bool ok = p < hw;
+  // all 2 x heads loads of this pixel are in flight together (they used to be serialised by two block barriers per head)
   float vals[16];
-  for (int h = 0; h < heads; ++h) {
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
     float v = 0.f;
-    if (ok) {
+    if (ok && h < heads) {
       const long long i = ((long long)b * heads + h) * hw + p;
       const float y = pred[i];
       v = dpred[i] * (1.f - y * y);
     }
     vals[h] = v;
-    float s = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int wv = 0; wv < 8; ++wv) t += sh[wv];
-      atomicAdd(dbias + h, t);
-    }
-    __syncthreads();
   }
   if (ok) {
     __nv_bfloat16* o = ds + ((long long)b * hw + p) * 16;
     uint32_t u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(2 * j < heads ? vals[2 * j] : 0.f, 2 * j + 1 < heads ? vals[2 * j + 1] : 0.f);
+    for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(vals[2 * j], vals[2 * j + 1]);
     reinterpret_cast<uint4*>(o)[0] = make_uint4(u[0], u[1], u[2], u[3]);
     reinterpret_cast<uint4*>(o)[1] = make_uint4(u[4], u[5], u[6], u[7]);
+  }
+  // bias gradients: warp sums -> one row per warp in shared memory -> 16 atomics per block
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
+    const float s = warp_sum(vals[h]);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][h] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < heads) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sh[wv][threadIdx.x];
+    atomicAdd(dbias + threadIdx.x, t);
   }
 }
 
