@@ -1173,7 +1173,9 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
           };
           double best = cost(256, 1.0);
           bn = 256;
-          if (a.n % 192 == 0 && !a.conv && !a.colstats && cost(192, 1.12) < best) { best = cost(192, 1.12); bn = 192; }
+          // 192-wide tiles move 14 % more operand bytes per flop; steady-state measurements (tools/gemm_roles.py: QKV at
+          // M=5264, 7 waves of 192 vs 6 of 256: 75.4 vs 73.3 us) put their break-even at 1.2x
+          if (a.n % 192 == 0 && !a.conv && !a.colstats && cost(192, 1.2) < best) { best = cost(192, 1.2); bn = 192; }
           if (cost(128, 1.25) < best) { best = cost(128, 1.25); bn = 128; }
           if (a.n % 256 != 0 && bn == 256 && a.n % 128 == 0 && a.n < 256) bn = 128;
         }
