@@ -112,6 +112,11 @@ typedef struct mv_gemm_args {
                          BatchNorm batch statistics of a train-mode conv; out may be NULL (statistics only) */
   int32_t kskip_begin, kskip_end; /* LINEAR: K range [begin, end) (multiples of 64) whose B columns are all zero and is
                                      not loaded at all (dT = [dQ | dK | dV] . [aB_q ; 0 ; aB_v]^T skips the dK third) */
+  int32_t ab_f16;     /* bit 0: A (and a2) hold fp16 instead of bf16, bit 1: B holds fp16 (kind::f16 takes either format
+                         per operand). The training-mode decoder keeps feature maps and conv weights in fp16: the
+                         reference trains under fp16 autocast (configs/config.yaml:23) and the LoRA gradients need the
+                         extra mantissa bits. Outputs are unaffected. */
+  int32_t reserved3;
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
@@ -127,8 +132,9 @@ void mv_gemm_set_profile_buffer(void* buf);
  *   bwd: dx[M, D] = dres + dLN(x, w)(dy); dy bf16 or fp32; dres optional; optional bf16 copy of dx.
  *        The affine parameters are frozen on this path (apply_lora, src/generators/lora.py:66-68): no dw / db.
  * ---------------------------------------------------------------------------------------------------------- */
-int mv_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, float* mean,
-                     float* rstd, int m, int d, float eps, void* stream);
+/* y_f16: store y as fp16 instead of bf16 (the final norm of the TRAINING forward feeds the fp16 decoder, see ab_f16) */
+int mv_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int y_f16,
+                     float* mean, float* rstd, int m, int d, float eps, void* stream);
 int mv_layernorm_bwd(const float* x, int64_t ldx, const float* w, const void* dy, int64_t lddy, int dy_f32,
                      const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, int m,
                      int d, float eps, void* stream);
@@ -151,16 +157,19 @@ int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, float* l
  *                     bicubic-resized (A=-0.75, align_corners False, scale factor target/grid) -> NHWC bf16.
  *   mv_upsample2x     Fusion_Block's bilinear x2 (mipheivit.py:89), NHWC bf16.
  * ---------------------------------------------------------------------------------------------------------- */
-int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk, void* stream);
+/* img_f16 / f16 flags below: the 16-bit maps are fp16 instead of bf16 (training-mode decoder, see mv_gemm_args.ab_f16);
+ * the patch matrix always stays bf16 (it meets the frozen bf16 ViT weights). */
+int mv_prep_input(const float* x, void* img_nhwc8, int img_f16, void* patch_matrix, int batch, int size, int ldk,
+                  void* stream);
 /* Input staging for whole-slide inference: raw uint8 H&E tiles NHWC [batch, size, size, 3] normalised on the
  * device, v = u8 * scale[c] + bias[c] with the H-Optimus statistics of src/dataset.py:600-601 (scale = 1/(255 std_c),
  * bias = -mean_c/std_c; HOST pointers to 3 floats each) — the H2D copy is 4x smaller than the fp32 NCHW tensor. */
-int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const float* bias3, void* img_nhwc8, void* patch_matrix,
-                     int batch, int size, int ldk, void* stream);
+int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const float* bias3, void* img_nhwc8, int img_f16,
+                     void* patch_matrix, int batch, int size, int ldk, void* stream);
 int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int batch, int n_tok, int n_prefix, int dim, void* stream);
 int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid, int target,
-                     int dim, void* stream);
-int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, void* stream);
+                     int dim, int f16, void* stream);
+int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, int f16, void* stream);
 
 /* adjoint of mv_tokens_to_map: d_map NHWC bf16 [B,t,t,D] -> d_tokens bf16 [B*n_tok, D] (prefix rows zero) */
 int mv_tokens_to_map_bwd(const void* dmap, void* dtokens, int64_t ldt, int batch, int n_tok, int prefix, int grid,
@@ -204,6 +213,31 @@ int mv_grad_norm(const float* grads, int64_t n, float max_norm, float* norm_out,
 int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* norm_coef, float grad_mul, float lr, float beta1, float beta2, float eps, int step,
                       void* stream);
+/* The same update with the step count and learning rate living on the DEVICE, so that a captured CUDA graph of the whole
+ * training step replays correctly:
+ *   mv_adam_schedule      *step (int64, optimiser steps taken so far) -> hyper[4] = {lr / (1 - beta1^t), sqrt(1 - beta2^t),
+ *                         lr, t} with t = *step + 1 and lr = base_lr * LambdaLR factor of pix2pix_lr_scheduler
+ *                         (src/utils.py:217-230 as built at src/models.py:363-369: linear warm-up, flat to total/2, linear to
+ *                         zero) evaluated at *step; then *step += 1.
+ *   mv_adam_clip_step_dev Adam update reading hyper[0..1] written by mv_adam_schedule. */
+int mv_adam_schedule(int64_t* step, float base_lr, int64_t total_steps, int64_t warmup_steps, float beta1, float beta2,
+                     float* hyper, void* stream);
+int mv_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const float* norm_coef, float grad_mul, const float* hyper, float beta1, float beta2, float eps,
+                          void* stream);
+/* Table-driven re-layout, dst[i] = convert(src[idx[i]]) (idx -1: zero, -2: leave dst[i]); mode 0 fp32, 1 bf16, 2 fp16.
+ * Packs the trainable decoder weights (reference layouts, one flat fp32 buffer) into the kernels' operand layouts and
+ * scatters the packed weight-gradient accumulators back into parameter layout — one launch per arena, no framework ops
+ * inside a training step.  mv_add_i64: BatchNorm num_batches_tracked counters (+= inc).  mv_memset_async: cudaMemsetAsync. */
+/* LoRA operands of every block from the flat parameter buffer, one launch: lora_flat fp32 [depth, 4, 8*d] = per block
+ * (A_q [d,8], B_q [8,d], A_v [d,8], B_v [8,d]) as QkvWithLoRA registers them (src/generators/lora.py:21-27); ptrs int64
+ * [depth, 4] = device pointers to the block's bf16 acat [16, d], K-extended QKV weight [3d, ldw] (columns d..d+15
+ * written), K-extended dX weight [d, ldb] (columns 3d..3d+15; may be 0) and bcat [16, 3d] (may be 0). */
+int mv_lora_refresh(const float* lora_flat, const int64_t* ptrs, int depth, int d, float alpha, int64_t ldw, int64_t ldb,
+                    void* stream);
+int mv_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, int mode, void* stream);
+int mv_add_i64(int64_t* p, int n, int64_t inc, void* stream);
+int mv_memset_async(void* p, int value, int64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Train-mode BatchNorm2d + ReLU around the convs (Basic_Conv3x3, src/generators/mipheivit.py:20-41; AttentionBlock.psi[1],
@@ -212,7 +246,8 @@ int mv_adam_clip_step(float* params, const float* grads, float* exp_avg, float* 
  *                     (momentum, unbiased variance). pre_bias: bias added before the BN (psi[0].bias) or NULL.
  *   mv_bn_relu_apply  y = relu(z*scale + shift); z is the raw conv output, bf16 or fp32 (z_f32) — the training path keeps
  *                     it in fp32 so that bf16 rounding does not flip ReLU masks against the fp32 reference
- *   mv_bn_relu_bwd    dz = BN'(dy * [y > 0]); sums (fp32 [2, C], overwritten) = (dbeta, dgamma)
+ *   mv_bn_relu_bwd    dz = BN'(dy * [y > 0]); sums (fp32 [2, C], overwritten) = (dbeta, dgamma); y may be bf16 or fp16
+ *                     (only its sign is read)
  * ---------------------------------------------------------------------------------------------------------- */
 int mv_bn_finalize(const float* colstats, double count, const float* gamma, const float* beta, const float* pre_bias,
                    float* running_mean, float* running_var, float momentum, float eps, int c, float* scale, float* shift,
@@ -223,18 +258,28 @@ int mv_bn_finalize(const float* colstats, double count, const float* gamma, cons
  *   mv_gram32             gram (fp32 [40, 32], zeroed by the caller): rows 0..31 += f^T f, row 32 += 1^T f; f bf16 [m, 32]
  *   mv_heads_bn_from_gram (gram, count = m) -> folded (scale, shift) for relu(scale * (W1 f) + shift), saved batch
  *                         (mean, rstd) of W1 f + b1, running-stat update; w1 fp32 [c, 32] = the weights the gate GEMM uses */
-int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, void* stream);
+int mv_gram32(const void* f, int64_t ldf, int64_t m, int f16, float* gram, void* stream);
+/* w1_fmt: W1 is rounded to the gate GEMM's operand format before use (0 none, 1 bf16, 2 fp16) */
 int mv_heads_bn_from_gram(const float* gram, double count, const float* w1, const float* b1, const float* gamma,
                           const float* beta, float* running_mean, float* running_var, float momentum, float eps, int c,
-                          float* scale, float* shift, float* mean, float* rstd, void* stream);
-int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int64_t m, int c,
-                     void* stream);
+                          float* scale, float* shift, float* mean, float* rstd, int w1_fmt, void* stream);
+/* Closed-form backward of the heads' gate MLP through its train-mode BatchNorm (csrc/heads_stats.cu): from
+ * E fp32 [40, 256] (rows 0..31 f^T e, row 32 1^T e), FF = the mv_gram32 output, fin = the [4, 256] (scale, shift, mean,
+ * rstd) of mv_heads_bn_from_gram and count = pixels:  dw1 [256, 32], dgamma / dbeta / dw2 [256] (parameter gradients of
+ * psi[0].weight, psi[1].weight / bias, psi[3].weight) and the operands of the two GEMMs that assemble d f:
+ * ca_t bf16 [32, 256], mx_n [32, 64] (fp16 when mx_f16 else bf16), kshift fp32 [32]. */
+int mv_heads_bwd_algebra(const float* E, const float* FF, const float* w1, const float* b1, const float* gamma,
+                         const float* w2, const float* fin, double count, int n_units, float* dw1, float* dgamma,
+                         float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* kshift, void* stream);
+int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int y_f16, int64_t m,
+                     int c, void* stream);
 int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, int z_f32, const float* mean, const float* rstd,
                    const float* gamma, float* sums, void* dz, int64_t m, int c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Memory-bound kernels of the decoder backward pass (csrc/decoder_bwd_ew.cu).
  * ---------------------------------------------------------------------------------------------------------- */
+/* 16-bit transpose; ones_row: 0 none, 1 append a row of bf16 ones, 2 a row of fp16 ones (fp16 data) */
 int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row, void* stream);
 int mv_upsample2x_bwd(const void* dup, int64_t ldu, void* dx, int batch, int h, int w, int c, void* stream);
 int mv_zero_insert2x(const void* dz, void* u, int batch, int h, int w, int c, void* stream);

@@ -37,6 +37,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ colstats, float cou
   }
 }
 
+// y > 0 on the raw 16-bit pattern: sign clear and not zero — the same test for bf16 and fp16 storage (ReLU outputs
+// are never NaN / inf), so the backward kernels take either format of the saved activation
+__device__ __forceinline__ bool pos16(uint32_t bits) { return bits != 0u && (bits & 0x8000u) == 0u; }
+
 // 8 consecutive channels of row-major z (bf16 or fp32) at vector index i
 template <bool ZF32>
 __device__ __forceinline__ void load_z8(const void* z, long long i, float* f) {
@@ -51,7 +55,7 @@ __device__ __forceinline__ void load_z8(const void* z, long long i, float* f) {
 }
 
 // one thread = 8 consecutive channels of one row
-template <bool ZF32>
+template <bool ZF32, bool F16>
 __global__ void bn_relu_apply_kernel(const void* __restrict__ z, const float* __restrict__ scale,
                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long M, int C) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
@@ -64,10 +68,10 @@ __global__ void bn_relu_apply_kernel(const void* __restrict__ z, const float* __
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
   const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
   uint4 o;
-  o.x = pack_bf16x2(fmaxf(f[0] * s0.x + h0.x, 0.f), fmaxf(f[1] * s0.y + h0.y, 0.f));
-  o.y = pack_bf16x2(fmaxf(f[2] * s0.z + h0.z, 0.f), fmaxf(f[3] * s0.w + h0.w, 0.f));
-  o.z = pack_bf16x2(fmaxf(f[4] * s1.x + h1.x, 0.f), fmaxf(f[5] * s1.y + h1.y, 0.f));
-  o.w = pack_bf16x2(fmaxf(f[6] * s1.z + h1.z, 0.f), fmaxf(f[7] * s1.w + h1.w, 0.f));
+  o.x = pack16x2<F16>(fmaxf(f[0] * s0.x + h0.x, 0.f), fmaxf(f[1] * s0.y + h0.y, 0.f));
+  o.y = pack16x2<F16>(fmaxf(f[2] * s0.z + h0.z, 0.f), fmaxf(f[3] * s0.w + h0.w, 0.f));
+  o.z = pack16x2<F16>(fmaxf(f[4] * s1.x + h1.x, 0.f), fmaxf(f[5] * s1.y + h1.y, 0.f));
+  o.w = pack16x2<F16>(fmaxf(f[6] * s1.z + h1.z, 0.f), fmaxf(f[7] * s1.w + h1.w, 0.f));
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
@@ -101,8 +105,8 @@ __global__ void __launch_bounds__(BNB_THREADS) bn_relu_bwd_stats_kernel(
       const uint32_t* pd = &ud.x; const uint32_t* py = &uy.x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]);
-        const float g0 = fy.x > 0.f ? fd.x : 0.f, g1 = fy.y > 0.f ? fd.y : 0.f;
+        const float2 fd = unpack_bf16x2(pd[j]);
+        const float g0 = pos16(py[j] & 0xFFFFu) ? fd.x : 0.f, g1 = pos16(py[j] >> 16) ? fd.y : 0.f;
         s1[2 * j] += g0; s1[2 * j + 1] += g1;
         s2[2 * j] += g0 * (fz[2 * j] - mu[2 * j]) * rs[2 * j];
         s2[2 * j + 1] += g1 * (fz[2 * j + 1] - mu[2 * j + 1]) * rs[2 * j + 1];
@@ -148,12 +152,12 @@ __global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, l
   uint32_t o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 fd = unpack_bf16x2(pd[j]), fy = unpack_bf16x2(py[j]);
+    const float2 fd = unpack_bf16x2(pd[j]);
     float r2[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int cc = c + 2 * j + e;
-      const float g = (e ? fy.y : fy.x) > 0.f ? (e ? fd.y : fd.x) : 0.f;
+      const float g = pos16(e ? py[j] >> 16 : py[j] & 0xFFFFu) ? (e ? fd.y : fd.x) : 0.f;
       const float xh = (fz[2 * j + e] - mean[cc]) * rstd[cc];
       r2[e] = gamma[cc] * rstd[cc] * (g - sums[cc] * inv_n - xh * sums[C + cc] * inv_n);
     }
@@ -177,16 +181,18 @@ extern "C" int mv_bn_finalize(const float* colstats, double count, const float* 
   return MV_OK;
 }
 
-extern "C" int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int64_t m, int c,
-                                void* stream_) {
+extern "C" int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int y_f16,
+                                int64_t m, int c, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(z && scale && shift && y && m > 0 && c % 8 == 0, "mv_bn_relu_apply: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = m * (c / 8);
-  if (z_f32) MV_LAUNCH((bn_relu_apply_kernel<true>), (unsigned)((total + 255) / 256), 256, 0, stream, 
-      z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
-  else MV_LAUNCH((bn_relu_apply_kernel<false>), (unsigned)((total + 255) / 256), 256, 0, stream, 
-      z, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), m, c);
+  const unsigned agrid = (unsigned)((total + 255) / 256);
+  __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+  if (z_f32 && y_f16) MV_LAUNCH((bn_relu_apply_kernel<true, true>), agrid, 256, 0, stream, z, scale, shift, yy, m, c);
+  else if (z_f32) MV_LAUNCH((bn_relu_apply_kernel<true, false>), agrid, 256, 0, stream, z, scale, shift, yy, m, c);
+  else if (y_f16) MV_LAUNCH((bn_relu_apply_kernel<false, true>), agrid, 256, 0, stream, z, scale, shift, yy, m, c);
+  else MV_LAUNCH((bn_relu_apply_kernel<false, false>), agrid, 256, 0, stream, z, scale, shift, yy, m, c);
   MV_CHECK_LAUNCH("bn_relu_apply");
   return MV_OK;
 }

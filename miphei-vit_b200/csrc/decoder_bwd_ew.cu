@@ -44,9 +44,10 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
     }
   }
   if (ones_row && blockIdx.y == 0) {
-    const __nv_bfloat16 one = __float2bfloat16(1.f);
+    // ones_row: 1 = bf16 data, 2 = fp16 data (the kernel only moves 16-bit words; the constant must match the format)
+    const unsigned short one = ones_row == 2 ? 0x3C00u : 0x3F80u;
     for (int i = threadIdx.y * 32 + threadIdx.x; i < 64; i += 32 * blockDim.y)
-      if (m0 + i < M) out[(long long)C * ldo + m0 + i] = one;
+      if (m0 + i < M) reinterpret_cast<unsigned short*>(out)[(long long)C * ldo + m0 + i] = one;
   }
 }
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ float in_px(const void* x, const InNorm& nm, long lon
   return reinterpret_cast<const float*>(x)[((b * 3 + c) * S + y) * (long long)S + xx];
 }
 
-template <bool U8>
+template <bool U8, bool F16>
 __global__ void prep_image_kernel(const void* __restrict__ x, InNorm nm, __nv_bfloat16* __restrict__ img, int B, int S) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   const long long npix = (long long)B * S * S;
@@ -35,8 +35,8 @@ __global__ void prep_image_kernel(const void* __restrict__ x, InNorm nm, __nv_bf
   const long long b = i / plane, r = i - b * plane;
   const int y = (int)(r / S), xx = (int)(r - (long long)y * S);
   uint4 o;
-  o.x = pack_bf16x2(in_px<U8>(x, nm, b, 0, y, xx, S), in_px<U8>(x, nm, b, 1, y, xx, S));
-  o.y = pack_bf16x2(in_px<U8>(x, nm, b, 2, y, xx, S), 0.f);
+  o.x = pack16x2<F16>(in_px<U8>(x, nm, b, 0, y, xx, S), in_px<U8>(x, nm, b, 1, y, xx, S));
+  o.y = pack16x2<F16>(in_px<U8>(x, nm, b, 2, y, xx, S), 0.f);
   o.z = 0u;
   o.w = 0u;
   reinterpret_cast<uint4*>(img)[i] = o;
@@ -85,6 +85,7 @@ __device__ __forceinline__ void cubic_coeffs(float t, float* w) {
 }
 
 // tokens bf16 [B, ntok, ldt] (prefix tokens first) -> out NHWC bf16 [B, t, t, D]; one block per output pixel
+template <bool F16>
 __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long long ldt, int ntok, int prefix, int g,
                                      int t, int D, float inv_scale, __nv_bfloat16* __restrict__ out) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
@@ -107,16 +108,16 @@ __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long
         const int xx = min(max(ix - 1 + e, 0), g - 1);
         const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)(yy * g + xx) * ldt + c);
         const float w = wy[a] * wx[e];
-        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        const float2 p0 = unpack16x2<F16>(u.x), p1 = unpack16x2<F16>(u.y), p2 = unpack16x2<F16>(u.z), p3 = unpack16x2<F16>(u.w);
         acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p1.x; acc[3] += w * p1.y;
         acc[4] += w * p2.x; acc[5] += w * p2.y; acc[6] += w * p3.x; acc[7] += w * p3.y;
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
+    o.x = pack16x2<F16>(acc[0], acc[1]);
+    o.y = pack16x2<F16>(acc[2], acc[3]);
+    o.z = pack16x2<F16>(acc[4], acc[5]);
+    o.w = pack16x2<F16>(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(out + (((long long)b * t + oy) * t + ox) * D + c) = o;
   }
 }
@@ -125,6 +126,7 @@ __global__ void tokens_to_map_kernel(const __nv_bfloat16* __restrict__ tok, long
 // One thread per (INPUT pixel, 8 channels) writes the 2x2 output block it centres: with clamped neighbours m = max(i-1, 0),
 // p = min(i+1, n-1) the exact x2 weights are  out(2i) = 0.25 in(m) + 0.75 in(i),  out(2i+1) = 0.75 in(i) + 0.25 in(p)  in both
 // directions (separable) — 9 sixteen-byte loads and one index decode per 4 outputs instead of 16 loads and 4 decodes.
+template <bool F16>
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h,
                                   int w, int C) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
@@ -150,7 +152,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
       const uint32_t* pu = &u.x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(pu[j]);
+        const float2 f = unpack16x2<F16>(pu[j]);
         v[a][q][2 * j] = f.x;
         v[a][q][2 * j + 1] = f.y;
       }
@@ -170,10 +172,10 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = dx == 0 ? 0.25f * t[0][j] + 0.75f * t[1][j] : 0.75f * t[1][j] + 0.25f * t[2][j];
       uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]);
-      u.y = pack_bf16x2(o[2], o[3]);
-      u.z = pack_bf16x2(o[4], o[5]);
-      u.w = pack_bf16x2(o[6], o[7]);
+      u.x = pack16x2<F16>(o[0], o[1]);
+      u.y = pack16x2<F16>(o[2], o[3]);
+      u.z = pack16x2<F16>(o[4], o[5]);
+      u.w = pack16x2<F16>(o[6], o[7]);
       *reinterpret_cast<uint4*>(ob + ((long long)dy * (2 * w) + dx) * C) = u;
     }
   }
@@ -260,12 +262,16 @@ extern "C" int mv_fill_prefix(float* x, int64_t ldx, const float* prefix, int ba
 
 namespace mv {
 template <bool U8>
-static int launch_prep(const void* x, const InNorm& nm, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
-                       cudaStream_t stream) {
+static int launch_prep(const void* x, const InNorm& nm, void* img_nhwc8, int img_f16, void* patch_matrix, int batch,
+                       int size, int ldk, cudaStream_t stream) {
   if (img_nhwc8) {
     const long long npix = (long long)batch * size * size;
-    MV_LAUNCH(prep_image_kernel<U8>, (unsigned)((npix + 255) / 256), 256, 0, stream, x, nm,
-              reinterpret_cast<__nv_bfloat16*>(img_nhwc8), batch, size);
+    if (img_f16)
+      MV_LAUNCH((prep_image_kernel<U8, true>), (unsigned)((npix + 255) / 256), 256, 0, stream, x, nm,
+                reinterpret_cast<__nv_bfloat16*>(img_nhwc8), batch, size);
+    else
+      MV_LAUNCH((prep_image_kernel<U8, false>), (unsigned)((npix + 255) / 256), 256, 0, stream, x, nm,
+                reinterpret_cast<__nv_bfloat16*>(img_nhwc8), batch, size);
     MV_CHECK_LAUNCH("prep_image");
   }
   if (patch_matrix) {
@@ -279,18 +285,18 @@ static int launch_prep(const void* x, const InNorm& nm, void* img_nhwc8, void* p
 }
 }  // namespace mv
 
-extern "C" int mv_prep_input(const float* x, void* img_nhwc8, void* patch_matrix, int batch, int size, int ldk,
-                             void* stream_) {
+extern "C" int mv_prep_input(const float* x, void* img_nhwc8, int img_f16, void* patch_matrix, int batch, int size,
+                             int ldk, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(x && batch > 0 && size >= 14, "mv_prep_input: null/empty");
   MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input: patch matrix pitch must be 592");
   InNorm nm = {{1.f, 1.f, 1.f}, {0.f, 0.f, 0.f}};
-  return launch_prep<false>(x, nm, img_nhwc8, patch_matrix, batch, size, ldk, reinterpret_cast<cudaStream_t>(stream_));
+  return launch_prep<false>(x, nm, img_nhwc8, img_f16, patch_matrix, batch, size, ldk, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 // raw uint8 H&E tiles, NHWC [B, S, S, 3]; v = u8 * scale[c] + bias[c] (scale = 1 / (255 std_c), bias = -mean_c / std_c)
 extern "C" int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const float* bias3, void* img_nhwc8,
-                                void* patch_matrix, int batch, int size, int ldk, void* stream_) {
+                                int img_f16, void* patch_matrix, int batch, int size, int ldk, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(tiles_u8 && scale3 && bias3 && batch > 0 && size >= 14, "mv_prep_input_u8: null/empty");
   MV_CHECK_ARG(!patch_matrix || ldk == 592, "mv_prep_input_u8: patch matrix pitch must be 592");
@@ -299,11 +305,12 @@ extern "C" int mv_prep_input_u8(const void* tiles_u8, const float* scale3, const
     nm.scale[c] = scale3[c];  // HOST pointers: six constants passed by value to the kernels
     nm.bias[c] = bias3[c];
   }
-  return launch_prep<true>(tiles_u8, nm, img_nhwc8, patch_matrix, batch, size, ldk, reinterpret_cast<cudaStream_t>(stream_));
+  return launch_prep<true>(tiles_u8, nm, img_nhwc8, img_f16, patch_matrix, batch, size, ldk,
+                           reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int batch, int n_tok, int prefix, int grid,
-                                int target, int dim, void* stream_) {
+                                int target, int dim, int f16, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(tokens && out && batch > 0, "mv_tokens_to_map: null/empty");
   MV_CHECK_ARG(n_tok == prefix + grid * grid && dim % 8 == 0 && ldt % 8 == 0, "mv_tokens_to_map: shape");
@@ -311,9 +318,14 @@ extern "C" int mv_tokens_to_map(const void* tokens, int64_t ldt, void* out, int 
   // PyTorch uses the reciprocal of the user-supplied scale factor (target/grid) for the source coordinates
   const float inv_scale = (float)(1.0 / ((double)target / (double)grid));
   const int threads = dim / 8 < 256 ? (dim / 8 + 31) / 32 * 32 : 256;
-  MV_LAUNCH(tokens_to_map_kernel, batch * target * target, threads, 0, stream, 
-      reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
-      reinterpret_cast<__nv_bfloat16*>(out));
+  if (f16)
+    MV_LAUNCH(tokens_to_map_kernel<true>, batch * target * target, threads, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
+              reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    MV_LAUNCH(tokens_to_map_kernel<false>, batch * target * target, threads, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(tokens), ldt, n_tok, prefix, grid, target, dim, inv_scale,
+              reinterpret_cast<__nv_bfloat16*>(out));
   MV_CHECK_LAUNCH("tokens_to_map");
   return MV_OK;
 }
@@ -334,13 +346,17 @@ extern "C" int mv_tokens_to_map_bwd(const void* dmap, void* dtokens, int64_t ldt
   return MV_OK;
 }
 
-extern "C" int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, void* stream_) {
+extern "C" int mv_upsample2x(const void* in, void* out, int batch, int h, int w, int c, int f16, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(in && out && batch > 0 && h > 0 && w > 0 && c % 8 == 0, "mv_upsample2x: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)batch * h * w * (c / 8);
-  MV_LAUNCH(upsample2x_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
-      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
+  if (f16)
+    MV_LAUNCH(upsample2x_kernel<true>, (unsigned)((total + 255) / 256), 256, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
+  else
+    MV_LAUNCH(upsample2x_kernel<false>, (unsigned)((total + 255) / 256), 256, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, c);
   MV_CHECK_LAUNCH("upsample2x");
   return MV_OK;
 }

@@ -66,6 +66,7 @@ struct GemmDev {
   //   [6] tiles of this CTA
   long long* prof;
   int kskip0, kskip1;  // k blocks [kskip0, kskip1) are skipped (their B columns are zero)
+  uint32_t idesc_clear;  // instruction-descriptor format bits to clear: bit 7 (A is fp16, not bf16), bit 10 (B is fp16)
 };
 
 // PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
@@ -378,7 +379,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N);
+      // a_format / b_format of kind::f16: 1 = bf16 (default), 0 = fp16 (training-mode decoder operands)
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N) & ~p.idesc_clear;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -413,7 +415,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else if constexpr (MODE == MV_GEMM_NN_ATOMIC) {
               // B is MN-major: 16 reduction rows = 2 KB per k step; all BLOCK_N columns (64-column swizzle atoms,
               // leading-dimension offset 8 KB) in ONE instruction
-              constexpr uint32_t idesc_mn = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 1);
+              const uint32_t idesc_mn = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 1) & ~p.idesc_clear;
               umma_bf16(d_tmem, da + 2 * k, db + (2048 >> 4) * k, idesc_mn, (kb != kb0) || (k != 0));
             } else if constexpr (PAIR) {
               umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
@@ -1043,6 +1045,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.prof = g_gemm_prof;
   p.kskip0 = a.kskip_begin / GEMM_BLOCK_K;
   p.kskip1 = a.kskip_end / GEMM_BLOCK_K;
+  p.idesc_clear = ((a.ab_f16 & 1) ? (1u << 7) : 0u) | ((a.ab_f16 & 2) ? (1u << 10) : 0u);
   if (MODE == MV_GEMM_NN_ATOMIC) {
     const int sms = device_sms() > 0 ? device_sms() : 148;
     const int mn = p.num_m_blocks * p.num_n_blocks;

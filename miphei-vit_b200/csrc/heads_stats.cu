@@ -21,13 +21,19 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+template <bool F16>
 __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // gram: fp32 [40, 32], pre-zeroed; rows 0..31 += f^T f, row 32 += 1^T f  (the layout the heads backward consumes)
+template <bool F16>
 __global__ void __launch_bounds__(GRAM_THREADS) gram32_kernel(const __nv_bfloat16* __restrict__ f, long long ldf, long long M,
                                                               float* __restrict__ gram) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram32_kernel(const __nv_bfloat1
       const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 x = unpack_bf16x2(w[j]);
+        const float2 x = unpack16x2<F16>(w[j]);
         csum[2 * j] += x.x;
         csum[2 * j + 1] += x.y;
       }
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram32_kernel(const __nv_bfloat1
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-          mma_bf16_16816(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], a[nt >> 1][nt & 1], a[nt >> 1][2 + (nt & 1)]);
+          mma_bf16_16816<F16>(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], a[nt >> 1][nt & 1], a[nt >> 1][2 + (nt & 1)]);
     }
     __syncwarp();
   }
@@ -130,7 +136,7 @@ __global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double
                                           const float* __restrict__ beta, float* __restrict__ running_mean,
                                           float* __restrict__ running_var, float momentum, float eps, int C,
                                           float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                          float* __restrict__ rstd_out) {
+                                          float* __restrict__ rstd_out, int w1_fmt) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ double cov[32 * 32];
   __shared__ double mf[32];
@@ -142,7 +148,11 @@ __global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double
   if (j >= C) return;
   double w[32];
 #pragma unroll
-  for (int a = 0; a < 32; ++a) w[a] = (double)w1[j * 32 + a];
+  for (int a = 0; a < 32; ++a) {
+    // the statistics must describe what the gate GEMM computes: W1 rounded to that GEMM's 16-bit operand format
+    const float wv = w1[j * 32 + a];
+    w[a] = w1_fmt == 1 ? (double)__bfloat162float(__float2bfloat16(wv)) : w1_fmt == 2 ? (double)__half2float(__float2half_rn(wv)) : (double)wv;
+  }
   double lin = 0.0, var = 0.0;
 #pragma unroll 4
   for (int a = 0; a < 32; ++a) {
@@ -167,9 +177,75 @@ __global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double
   }
 }
 
+// Closed-form gradients of the 16 SegmentationHead gates (AttentionBlock.psi = conv1x1 -> BatchNorm(batch statistics) ->
+// ReLU -> conv1x1 -> sigmoid, src/generators/unet.py:407-422) from three small moment matrices, one CTA:
+//   E  [40, 256]: rows 0..31 = f^T e, row 32 = 1^T e   (e = gate-unit gradient masked by the ReLU, bf16 [M, 256])
+//   FF [40, 32] : rows 0..31 = f^T f, row 32 = 1^T f
+// with a = W1 f + b1, ahat = (a - mean) rstd, the BatchNorm backward folds into
+//   dW1 = gr (w2 EF - S1/n F1 - S2/n XF),  d gamma = S2,  d beta = S1,  d w2 = scale A + shift E1
+//   d f  = dt W3t + e Ca - f Mx - (K0 + K1)          (Ca, Mx, K0 + K1 are written as the operands of the two GEMMs
+//                                                     that form d f: CaT bf16 [32, 256], MxN fp16/bf16 [32, 64], kshift [32])
+// Everything is fp32; unit j = 16 * head + hidden index; units >= n_units are skipped.
+__global__ void __launch_bounds__(256) heads_bwd_algebra_kernel(
+    const float* __restrict__ E, const float* __restrict__ FF, const float* __restrict__ W1, const float* __restrict__ b1,
+    const float* __restrict__ gam, const float* __restrict__ w2, const float* __restrict__ fin, float n, int n_units,
+    float* __restrict__ dW1, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
+    __nv_bfloat16* __restrict__ CaT, void* __restrict__ MxN, int mx_f16, float* __restrict__ kshift) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  __shared__ float F2s[32 * 33], F1s[32], Ws[256 * 33], kr[256], K01[32];
+  const int j = threadIdx.x;
+  for (int i = j; i < 32 * 32; i += 256) F2s[(i >> 5) * 33 + (i & 31)] = FF[i];
+  if (j < 32) { F1s[j] = FF[32 * 32 + j]; K01[j] = 0.f; }
+  const bool on = j < n_units;
+  for (int c = 0; c < 32; ++c) Ws[j * 33 + c] = on ? W1[j * 32 + c] : 0.f;
+  __syncthreads();
+  const float* scale_g = fin;
+  const float* shift_g = fin + 256;
+  const float* mean = fin + 512;
+  const float* rstd = fin + 768;
+  float k2r = 0.f;
+  if (on) {
+    const float rs = rstd[j], bm = b1[j] - mean[j], g = gam[j] * rs, ww = w2[j];
+    const float E1 = E[32 * 256 + j];
+    float A = 0.f;
+    for (int c = 0; c < 32; ++c) A += Ws[j * 33 + c] * E[c * 256 + j];
+    const float S1 = ww * E1;
+    const float S2 = ww * rs * (A + bm * E1);
+    dbeta[j] = S1;
+    dgamma[j] = S2;
+    dw2[j] = scale_g[j] * A + shift_g[j] * E1;
+    const float s1n = S1 / n, s2n = S2 / n;
+    for (int c = 0; c < 32; ++c) {
+      float wf = 0.f;
+      for (int a = 0; a < 32; ++a) wf += Ws[j * 33 + a] * F2s[a * 33 + c];
+      const float xf = rs * (wf + bm * F1s[c]);
+      dW1[j * 32 + c] = g * (ww * E[c * 256 + j] - s1n * F1s[c] - s2n * xf);
+      CaT[c * 256 + j] = __float2bfloat16(g * ww * Ws[j * 33 + c]);
+    }
+    const float k2 = g * s2n;
+    k2r = k2 * rs;
+    const float k01 = g * s1n + k2r * bm;  // K0 + K1 share the factor W1[j, c]
+    for (int c = 0; c < 32; ++c) atomicAdd(&K01[c], k01 * Ws[j * 33 + c]);
+  } else {
+    for (int c = 0; c < 32; ++c) CaT[c * 256 + j] = __float2bfloat16(0.f);
+  }
+  kr[j] = k2r;
+  __syncthreads();
+  if (j < 32) kshift[j] = -K01[j];
+  // MxN[r, c] = -Mx[c, r] = -sum_j W1[j, c] k2r_j W1[j, r]   (B operand [N = 32, K = 32 of pitch 64] of  dy = f (-Mx) + ...)
+  for (int i = j; i < 32 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    float acc = 0.f;
+    if (c < 32)
+      for (int u = 0; u < n_units; ++u) acc += Ws[u * 33 + c] * kr[u] * Ws[u * 33 + r];
+    if (mx_f16) reinterpret_cast<__half*>(MxN)[i] = __float2half_rn(-acc);
+    else reinterpret_cast<__nv_bfloat16*>(MxN)[i] = __float2bfloat16(-acc);
+  }
+}
+
 }  // namespace mv
 
-extern "C" int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, void* stream_) {
+extern "C" int mv_gram32(const void* f, int64_t ldf, int64_t m, int f16, float* gram, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(f && gram && m > 0, "mv_gram32: null/empty");
   MV_CHECK_ARG(ldf >= 32 && ldf % 8 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "mv_gram32: rows of 32 bf16, 16-byte aligned");
@@ -178,21 +254,38 @@ extern "C" int mv_gram32(const void* f, int64_t ldf, int64_t m, float* gram, voi
   const int sms = device_sms() > 0 ? device_sms() : 148;
   long long grid = (nchunks + (GRAM_THREADS / 32) - 1) / (GRAM_THREADS / 32);
   if (grid > 4ll * sms) grid = 4ll * sms;
-  MV_LAUNCH(gram32_kernel, (unsigned)grid, GRAM_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
+  if (f16) MV_LAUNCH(gram32_kernel<true>, (unsigned)grid, GRAM_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
+  else MV_LAUNCH(gram32_kernel<false>, (unsigned)grid, GRAM_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(f), ldf, m, gram);
   MV_CHECK_LAUNCH("gram32");
   return MV_OK;
 }
 
 extern "C" int mv_heads_bn_from_gram(const float* gram, double count, const float* w1, const float* b1, const float* gamma,
                                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                                     int c, float* scale, float* shift, float* mean, float* rstd, void* stream_) {
+                                     int c, float* scale, float* shift, float* mean, float* rstd, int w1_fmt,
+                                     void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(gram && w1 && b1 && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0,
                "mv_heads_bn_from_gram: null/empty");
   MV_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "mv_heads_bn_from_gram: running stats go together");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MV_LAUNCH(heads_bn_from_gram_kernel, (c + 63) / 64, 64, 0, stream, gram, count, w1, b1, gamma, beta, running_mean, running_var,
-                                                             momentum, eps, c, scale, shift, mean, rstd);
+                                                             momentum, eps, c, scale, shift, mean, rstd, w1_fmt);
   MV_CHECK_LAUNCH("heads_bn_from_gram");
+  return MV_OK;
+}
+
+extern "C" int mv_heads_bwd_algebra(const float* E, const float* FF, const float* w1, const float* b1, const float* gamma,
+                                    const float* w2, const float* fin, double count, int n_units, float* dw1, float* dgamma,
+                                    float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* kshift,
+                                    void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(E && FF && w1 && b1 && gamma && w2 && fin && dw1 && dgamma && dbeta && dw2 && ca_t_bf16 && mx_n && kshift,
+               "mv_heads_bwd_algebra: null pointer");
+  MV_CHECK_ARG(n_units > 0 && n_units <= 256 && count > 0, "mv_heads_bwd_algebra: n_units in 1..256");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MV_LAUNCH(heads_bwd_algebra_kernel, 1, 256, 0, stream, E, FF, w1, b1, gamma, w2, fin, (float)count, n_units, dw1, dgamma,
+            dbeta, dw2, reinterpret_cast<__nv_bfloat16*>(ca_t_bf16), mx_n, mx_f16, kshift);
+  MV_CHECK_LAUNCH("heads_bwd_algebra");
   return MV_OK;
 }

@@ -12,7 +12,7 @@ namespace mv {
 
 constexpr int LN_WARPS = 8;
 
-template <int V>  // V float4 per lane: D = 128 * V
+template <int V, bool F16 = false>  // V float4 per lane: D = 128 * V; F16: y stored as fp16 (training decoder input)
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                                       const float* __restrict__ w,
                                                                       const float* __restrict__ b,
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
   for (int i = 0; i < V; ++i) {
     const float4 ww = __ldg(wr + i * 32 + lane), bb = __ldg(br + i * 32 + lane);
     uint2 o;
-    o.x = pack_bf16x2((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
-    o.y = pack_bf16x2((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+    o.x = pack16x2<F16>((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
+    o.y = pack16x2<F16>((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
     yr[i * 32 + lane] = o;
   }
 }
@@ -143,15 +143,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
   }
 
 extern "C" int mv_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy,
-                                float* mean, float* rstd, int m, int d, float eps, void* stream_) {
+                                int y_f16, float* mean, float* rstd, int m, int d, float eps, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(x && w && b && y && m > 0, "mv_layernorm_fwd: null/empty");
   MV_CHECK_ARG(d % 128 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "mv_layernorm_fwd: D %% 128, ldx %% 4, ldy %% 4");
   MV_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mv_layernorm_fwd: mean and rstd go together");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = (m + LN_WARPS - 1) / LN_WARPS;
-  MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_fwd_kernel<V>), grid, LN_WARPS * 32, 0, stream, 
-                              x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, m, eps)));
+  if (y_f16) {
+    MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_fwd_kernel<V, true>), grid, LN_WARPS * 32, 0, stream,
+                                x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, m, eps)));
+  } else {
+    MV_LN_DISPATCH(d / 128, (MV_LAUNCH((layernorm_fwd_kernel<V>), grid, LN_WARPS * 32, 0, stream,
+                                x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, m, eps)));
+  }
   MV_CHECK_LAUNCH("layernorm_fwd");
   return MV_OK;
 }

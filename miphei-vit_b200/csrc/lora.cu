@@ -48,6 +48,40 @@ __global__ void lora_unpack_kernel(const float* __restrict__ g_a, const float* _
   dBv[(long long)r * D + d] = alpha * g_b[(long long)(8 + r) * 3 * D + 2 * D + d];
 }
 
+// LoRA operand refresh for ALL blocks in one launch.  src: flat fp32 [depth, 4, 8*D] = per block (A_q [D,8], B_q [8,D],
+// A_v [D,8], B_v [8,D]) in parameter layout; ptrs: int64 [depth, 4] device pointers to the block's bf16 operands
+//   acat [16, D]            = [A_q | A_v]^T                                     (B operand of T = xn [A_q | A_v])
+//   wqkv_ext [3D, ldw]      columns D..D+15: alpha B_q^T on the q rows, alpha B_v^T on the v rows (K-extended QKV weight)
+//   wqkv_bwd_ext [D, ldb]   columns 3D..3D+15: [A_q | A_v]                     (K-extended dX weight; may be null)
+//   bcat [16, 3D]           = [alpha B_q ; 0 ; alpha B_v] blocks                (B operand of dT; may be null)
+__global__ void lora_refresh_kernel(const float* __restrict__ src, const long long* __restrict__ ptrs, int D, float alpha,
+                                    long long ldw, long long ldb) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  const int blk = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 8 * D) return;
+  const int r = e / D, d = e - r * D;
+  const float* s = src + (long long)blk * 32 * D;
+  const float aq = s[d * 8 + r], av = s[16ll * D + d * 8 + r];
+  const float bq = alpha * s[8ll * D + (long long)r * D + d], bv = alpha * s[24ll * D + (long long)r * D + d];
+  __nv_bfloat16* acat = reinterpret_cast<__nv_bfloat16*>(ptrs[blk * 4 + 0]);
+  __nv_bfloat16* wext = reinterpret_cast<__nv_bfloat16*>(ptrs[blk * 4 + 1]);
+  __nv_bfloat16* wbwd = reinterpret_cast<__nv_bfloat16*>(ptrs[blk * 4 + 2]);
+  __nv_bfloat16* bcat = reinterpret_cast<__nv_bfloat16*>(ptrs[blk * 4 + 3]);
+  acat[(long long)r * D + d] = __float2bfloat16(aq);
+  acat[(long long)(8 + r) * D + d] = __float2bfloat16(av);
+  wext[(long long)d * ldw + D + r] = __float2bfloat16(bq);
+  wext[(long long)(2 * D + d) * ldw + D + 8 + r] = __float2bfloat16(bv);
+  if (wbwd) {
+    wbwd[(long long)d * ldb + 3 * D + r] = __float2bfloat16(aq);
+    wbwd[(long long)d * ldb + 3 * D + 8 + r] = __float2bfloat16(av);
+  }
+  if (bcat) {
+    bcat[(long long)r * 3 * D + d] = __float2bfloat16(bq);
+    bcat[(long long)(8 + r) * 3 * D + 2 * D + d] = __float2bfloat16(bv);
+  }
+}
+
 }  // namespace mv
 
 extern "C" int64_t mv_lora_grads_workspace_bytes(int m, int d) {
@@ -101,5 +135,17 @@ extern "C" int mv_lora_grads(const void* xn_ext, int64_t ldx, const void* dqkv_e
   if (rc) return rc;
   MV_LAUNCH(lora_unpack_kernel, (8 * d + 255) / 256, 256, 0, stream, g_a, g_b, dA_q, dA_v, dB_q, dB_v, d, alpha);
   MV_CHECK_LAUNCH("lora_unpack");
+  return MV_OK;
+}
+
+extern "C" int mv_lora_refresh(const float* lora_flat, const int64_t* ptrs, int depth, int d, float alpha, int64_t ldw,
+                               int64_t ldb, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(lora_flat && ptrs && depth > 0 && d > 0 && d % 8 == 0, "mv_lora_refresh: null/empty");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid((8 * d + 255) / 256, depth);
+  MV_LAUNCH(lora_refresh_kernel, grid, 256, 0, stream, lora_flat, reinterpret_cast<const long long*>(ptrs), d, alpha,
+            (long long)ldw, (long long)ldb);
+  MV_CHECK_LAUNCH("lora_refresh");
   return MV_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace mv {
@@ -266,6 +267,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
+}
+// 16-bit storage format chosen at compile time: bf16 (default everywhere) or fp16 (the training-mode decoder keeps its
+// feature maps / conv operands in fp16 — 3 more mantissa bits, values are O(1) post-BatchNorm activations; kind::f16 UMMA
+// takes either format per operand)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if (F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t u) {
+  if (F16) {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(h);
+  }
+  return unpack_bf16x2(u);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

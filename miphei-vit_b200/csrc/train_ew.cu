@@ -149,6 +149,74 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
   }
 }
 
+// dst[i] = convert(src[idx[i]]): weight re-layout (reference parameter layout -> kernel operand layouts) and gradient
+// re-layout (packed weight-gradient accumulators -> parameter layout) as ONE table-driven launch per arena, so that a
+// training step contains no framework-side tensor ops.  idx[i] = -1 writes zero, -2 leaves dst[i] untouched.
+//   mode 0: fp32 copy   1: bf16   2: fp16
+template <int MODE>
+__global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                          void* __restrict__ dst, long long n) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = idx[i];
+    if (j == -2) continue;
+    const float v = j >= 0 ? src[j] : 0.f;
+    if (MODE == 0) reinterpret_cast<float*>(dst)[i] = v;
+    else if (MODE == 1) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(v);
+    else reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void add_i64_kernel(long long* __restrict__ p, int n, long long inc) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += inc;
+}
+
+// LambdaLR factor of pix2pix_lr_scheduler (src/utils.py:217-230) as configure_optimizers builds it (src/models.py:
+// 363-369: warm-up 400 steps, flat to total/2, linear to zero) and Adam's bias corrections for step t = *step + 1;
+// hyper = {lr / (1 - beta1^t), sqrt(1 - beta2^t), lr, t}; then *step += 1.  One thread: the step lives on the device so
+// that a captured CUDA graph of the training step replays with the right learning rate.
+__global__ void adam_schedule_kernel(long long* __restrict__ step, float base_lr, long long total_steps,
+                                     long long warmup_steps, float beta1, float beta2, float* __restrict__ hyper) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long s = *step;  // optimiser steps taken so far: LambdaLR evaluates the factor at s, Adam's t is s + 1
+  const long long half = total_steps / 2;
+  double f;
+  if (s < warmup_steps) f = (double)s / (double)(warmup_steps > 1 ? warmup_steps : 1);
+  else if (s < half) f = 1.0;
+  else {
+    f = (double)(total_steps - s) / (double)(total_steps - half > 1 ? total_steps - half : 1);
+    if (f < 0.0) f = 0.0;
+  }
+  const double lr = (double)base_lr * f;
+  const double t = (double)(s + 1);
+  hyper[0] = (float)(lr / (1.0 - pow((double)beta1, t)));
+  hyper[1] = (float)sqrt(1.0 - pow((double)beta2, t));
+  hyper[2] = (float)lr;
+  hyper[3] = (float)t;
+  *step = s + 1;
+}
+
+__global__ void __launch_bounds__(256) adam_clip_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                            float* __restrict__ m, float* __restrict__ v, long long n,
+                                                            const float* __restrict__ norm_coef, float grad_mul,
+                                                            const float* __restrict__ hyper, float beta1, float beta2,
+                                                            float eps) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  const float coef = (norm_coef ? norm_coef[1] : 1.f) * grad_mul;
+  const float step = hyper[0], bc2_sqrt = hyper[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
 }  // namespace mv
 
 extern "C" int mv_loss_fwd_bwd(const float* pred, const float* target, float* grad, const float* weights, int batch,
@@ -211,5 +279,65 @@ extern "C" int mv_adam_clip_step(float* params, const float* grads, float* exp_a
   MV_LAUNCH(adam_clip_kernel, blocks, 256, 0, stream, params, grads, exp_avg, exp_avg_sq, n, norm_coef, grad_mul, lr, beta1, beta2,
                                                eps, (float)bc1, (float)sqrt(bc2));
   MV_CHECK_LAUNCH("adam_clip");
+  return MV_OK;
+}
+
+extern "C" int mv_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, int mode, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(src && idx && dst && n > 0 && mode >= 0 && mode <= 2, "mv_gather_cast: null/empty or bad mode");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int blocks = (int)((n + 255) / 256);
+  const int cap = (device_sms() > 0 ? device_sms() : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (mode == 0) MV_LAUNCH(gather_cast_kernel<0>, blocks, 256, 0, stream, src, idx, dst, (long long)n);
+  else if (mode == 1) MV_LAUNCH(gather_cast_kernel<1>, blocks, 256, 0, stream, src, idx, dst, (long long)n);
+  else MV_LAUNCH(gather_cast_kernel<2>, blocks, 256, 0, stream, src, idx, dst, (long long)n);
+  MV_CHECK_LAUNCH("gather_cast");
+  return MV_OK;
+}
+
+extern "C" int mv_add_i64(int64_t* p, int n, int64_t inc, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(p && n > 0, "mv_add_i64: null/empty");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MV_LAUNCH(add_i64_kernel, (n + 127) / 128, 128, 0, stream, reinterpret_cast<long long*>(p), n, (long long)inc);
+  MV_CHECK_LAUNCH("add_i64");
+  return MV_OK;
+}
+
+extern "C" int mv_memset_async(void* p, int value, int64_t bytes, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(p && bytes > 0, "mv_memset_async: null/empty");
+  cudaError_t e = cudaMemsetAsync(p, value, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream_));
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return MV_OK;
+}
+
+extern "C" int mv_adam_schedule(int64_t* step, float base_lr, int64_t total_steps, int64_t warmup_steps, float beta1,
+                                float beta2, float* hyper, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(step && hyper && total_steps > 0, "mv_adam_schedule: null/empty");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MV_LAUNCH(adam_schedule_kernel, 1, 32, 0, stream, reinterpret_cast<long long*>(step), base_lr, (long long)total_steps,
+            (long long)warmup_steps, beta1, beta2, hyper);
+  MV_CHECK_LAUNCH("adam_schedule");
+  return MV_OK;
+}
+
+extern "C" int mv_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                     const float* norm_coef, float grad_mul, const float* hyper, float beta1, float beta2,
+                                     float eps, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && hyper && n > 0, "mv_adam_clip_step_dev: null/empty");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int blocks = (int)((n + 255) / 256);
+  const int cap = (device_sms() > 0 ? device_sms() : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  MV_LAUNCH(adam_clip_dev_kernel, blocks, 256, 0, stream, params, grads, exp_avg, exp_avg_sq, (long long)n, norm_coef, grad_mul,
+            hyper, beta1, beta2, eps);
+  MV_CHECK_LAUNCH("adam_clip_dev");
   return MV_OK;
 }

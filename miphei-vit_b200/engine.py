@@ -81,6 +81,11 @@ class MipheiEngine:
         # which removes the x @ [A_q | A_v] GEMM and the 16 extra K columns from every block of the frozen forward
         self.merge_lora_eval = True
         self._merged_versions = None
+        # trainer mode: (flat parameters, flat gradients, decoder segment length) — every trainable parameter is a view of
+        # the first buffer (decoder segment first, then the LoRA matrices block by block), see trainer.FlatParams
+        self.flat_params = None
+        self._lora_src = None
+        self._lora_ptrs = None
 
     # ------------------------------------------------------------------ geometry
     def _geometry(self):
@@ -107,6 +112,11 @@ class MipheiEngine:
         self._lora_bwd_versions = None
         self._dec_train_versions = None
         self._merged_versions = None
+        # the training decoder re-binds BatchNorm buffers to views of its own vectors and caches device pointers: after
+        # model.to() / .half() / load (every caller of invalidate) it is rebuilt from the module's current tensors
+        self.decoder_train = None
+        self._lora_src = None
+        self._lora_ptrs = None
 
     def _train_tape(self, B):
         tape = self._tapes.get(B)
@@ -127,9 +137,7 @@ class MipheiEngine:
 
     def _pack_frozen(self):
         self._geometry()
-        if self.device.type != "cuda":
-            raise ops._lib.MipheiB200Error("the MIPHEI-ViT B200 engine needs its parameters on a CUDA device (got %s); "
-                                           "there is no CPU path" % self.device)
+        ops.require_cuda(self.device, "the MIPHEI-ViT B200 engine (its parameters)")
         vit = self.model.encoder.vit
         D = self.D
         with torch.no_grad():
@@ -165,16 +173,30 @@ class MipheiEngine:
         self._packed = True
         self._train_versions = None
 
-    def _pack_lora(self):
-        """LoRA columns of the K-extended QKV weight (forward)."""
-        D = self.D
-        with torch.no_grad():
-            for pb in self.blocks:
-                lq, lv = pb["lora"]
-                pb["acat"][:8] = lq.A.detach().t()
-                pb["acat"][8:] = lv.A.detach().t()
-                pb["wqkv_ext"][:D, D:D + 8] = (lq.alpha * lq.B.detach()).t()
-                pb["wqkv_ext"][2 * D:, D + 8:D + 16] = (lv.alpha * lv.B.detach()).t()
+    def refresh_lora_operands(self):
+        """LoRA columns of the K-extended QKV weights (forward) and, once the backward weights exist, of the dX / dT
+        operands — all blocks in ONE kernel launch reading the flat parameter buffer (mv_lora_refresh)."""
+        D, L = self.D, self.depth
+        if self.flat_params is not None:
+            flat, _, n_dec = self.flat_params
+            src = flat[n_dec:n_dec + L * 32 * D]
+        else:
+            if self._lora_src is None:
+                self._lora_src = torch.zeros(L * 32 * D, dtype=torch.float32, device=self.device)
+            src = self._lora_src
+            with torch.no_grad():
+                v = src.view(L, 4, 8 * D)
+                for i, pb in enumerate(self.blocks):
+                    lq, lv = pb["lora"]
+                    for j, t in enumerate((lq.A, lq.B, lv.A, lv.B)):
+                        v[i, j].copy_(t.detach().reshape(-1))
+        bwd = bool(getattr(self, "_bwd_packed", False))
+        if self._lora_ptrs is None or self._lora_ptrs[1] != bwd:
+            tab = [[pb["acat"].data_ptr(), pb["wqkv_ext"].data_ptr(), pb["wqkv_bwd_ext"].data_ptr() if bwd else 0,
+                    pb["bcat"].data_ptr() if bwd else 0] for pb in self.blocks]
+            self._lora_ptrs = (torch.tensor(tab, dtype=torch.int64, device=self.device), bwd)
+        alpha = self.blocks[0]["lora"][0].alpha
+        ops.lora_refresh(src, self._lora_ptrs[0], L, D, alpha, D + 64, 3 * D + 64)
 
     def _pack_lora_merged(self):
         """Eval-only QKV weight with the LoRA updates folded in (fp32 sum, one bf16 rounding)."""
@@ -222,8 +244,10 @@ class MipheiEngine:
             self._lora_versions = None
         ver = self._trainable_version()
         if self._lora_versions != ver:
-            self._pack_lora()
+            self.refresh_lora_operands()
             self._lora_versions = ver
+            if getattr(self, "_bwd_packed", False):
+                self._lora_bwd_versions = ver
         if not train and self.merge_lora_eval and self._merged_versions != ver:
             self._pack_lora_merged()
             self._merged_versions = ver
@@ -382,8 +406,7 @@ class MipheiEngine:
             raise AssertionError("Input size (%s) doesn't match model (%d)" % (tuple(x.shape), self.S))
 
     def _check_input(self, x):
-        if not x.is_cuda:
-            raise ops._lib.MipheiB200Error("MIPHEI-ViT B200 generator needs CUDA inputs (got %s); no CPU path" % x.device)
+        ops.require_cuda(x.device, "the MIPHEI-ViT B200 generator (its input)")
         self._check_input_shape(x)
 
     def forward(self, x):

@@ -38,6 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("reserved_splits", c_i32), ("reserved2", c_i32),
         ("colstats", c_void_p),
         ("kskip_begin", c_i32), ("kskip_end", c_i32),
+        ("ab_f16", c_i32), ("reserved3", c_i32),
     ]
 
 
@@ -51,17 +52,17 @@ _SIGNATURES = {
     "mv_reset_launch_count": (None, []),
     "mv_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "mv_gemm_set_profile_buffer": (None, [c_void_p]),
-    "mv_layernorm_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int,
+    "mv_layernorm_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_float, c_void_p]),
     "mv_layernorm_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
                                  c_void_p, c_i64, c_int, c_int, c_float, c_void_p]),
     "mv_attn_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
-    "mv_prep_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "mv_prep_input_u8": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p, c_int, c_int,
-                                 c_int, c_void_p]),
+    "mv_prep_input": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv_prep_input_u8": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int, c_void_p, c_int,
+                                 c_int, c_int, c_void_p]),
     "mv_fill_prefix": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "mv_tokens_to_map": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "mv_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_tokens_to_map": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mv_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_tokens_to_map_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_attn_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
                             c_int, c_int, c_int, c_float, c_void_p]),
@@ -70,10 +71,20 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_i64, c_void_p]),
     "mv_bn_finalize": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mv_gram32": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
+    "mv_gram32": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p]),
     "mv_heads_bn_from_gram": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mv_bn_relu_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+                                      c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "mv_heads_bwd_algebra": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_void_p]),
+    "mv_adam_schedule": (c_int, [c_void_p, c_float, c_i64, c_i64, c_float, c_float, c_void_p, c_void_p]),
+    "mv_adam_clip_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_void_p, c_float,
+                                      c_float, c_float, c_void_p]),
+    "mv_lora_refresh": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_i64, c_i64, c_void_p]),
+    "mv_gather_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mv_add_i64": (c_int, [c_void_p, c_int, c_i64, c_void_p]),
+    "mv_memset_async": (c_int, [c_void_p, c_int, c_i64, c_void_p]),
+    "mv_bn_relu_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p]),
     "mv_bn_relu_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_i64, c_int, c_void_p]),
     "mv_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),

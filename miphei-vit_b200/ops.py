@@ -6,6 +6,7 @@ import torch
 
 from . import lib as _lib
 
+_H16 = (torch.bfloat16, torch.float16)
 GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD, GEMM_HEAD_GATE, GEMM_HEAD_CONV, GEMM_NN_ATOMIC = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU, ACT_GATE_MASK = 0, 1, 2
 
@@ -18,9 +19,14 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def require_cuda(device, what):
+    """Every entry into the kernels goes through here: no CUDA device, no computation (there is no CPU path)."""
+    if device.type != "cuda":
+        raise _lib.MipheiB200Error("%s needs a CUDA device (got %s); miphei_b200 has no CPU path" % (what, device))
+
+
 def _lib_for(t):
-    if not t.is_cuda:
-        raise _lib.MipheiB200Error("miphei_b200 ops need CUDA tensors (got %s); there is no CPU path" % t.device)
+    require_cuda(t.device, "miphei_b200 ops")
     return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
@@ -36,7 +42,8 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
          kskip=None):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
     lib = _lib_for(a)
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    # 16-bit operands: bf16 (default) or fp16 (training-mode decoder maps / weights); the formats are independent
+    assert a.dtype in _H16 and b.dtype in _H16
     if mode == GEMM_NN_ATOMIC and conv is not None:
         N = Kb = None
     elif mode == GEMM_NN_ATOMIC:
@@ -124,6 +131,13 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     args.resid_row_mod = 1 if resid_row_mod else 0
     args.block_n = block_n
     args.reserved2 = pair  # 0 auto, 1 never, 2 always: CTA-pair (cta_group::2) tiles
+    a2t = conv.get("a2") if conv is not None else None
+    if conv is not None and mode == GEMM_NN_ATOMIC:  # wgrad: b (and a2) are the NHWC maps, both read as the B operand
+        assert a2t is None or a2t.dtype == b.dtype
+        args.ab_f16 = (1 if a.dtype == torch.float16 else 0) | (2 if b.dtype == torch.float16 else 0)
+    else:
+        assert a2t is None or a2t.dtype == a.dtype
+        args.ab_f16 = (1 if a.dtype == torch.float16 else 0) | (2 if b.dtype == torch.float16 else 0)
     if kskip is not None:  # K range with all-zero B columns: never loaded
         args.kskip_begin, args.kskip_end = int(kskip[0]), int(kskip[1])
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")
@@ -142,8 +156,10 @@ def layernorm_fwd(x, w, b, *, out=None, eps=1e-6, stats=False):
     if stats:
         mean = torch.empty(M, dtype=torch.float32, device=x.device)
         rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-    _lib.check(lib.mv_layernorm_fwd(_ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(out), out.stride(0), _ptr(mean),
-                                    _ptr(rstd), M, D, eps, _stream()), "mv_layernorm_fwd")
+    assert out.dtype in _H16
+    _lib.check(lib.mv_layernorm_fwd(_ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(out), out.stride(0),
+                                    1 if out.dtype == torch.float16 else 0, _ptr(mean), _ptr(rstd), M, D, eps, _stream()),
+               "mv_layernorm_fwd")
     return (out, mean, rstd) if stats else out
 
 
@@ -188,7 +204,8 @@ def prep_input(x, want_image=True, want_patches=True, img=None, pm=None):
         img = torch.empty((B, S, S, 8), dtype=torch.bfloat16, device=x.device)
     if pm is None and want_patches:
         pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.mv_prep_input(_ptr(x), _ptr(img), _ptr(pm), B, S, 592, _stream()), "mv_prep_input")
+    f16 = 1 if (img is not None and img.dtype == torch.float16) else 0
+    _lib.check(lib.mv_prep_input(_ptr(x), _ptr(img), f16, _ptr(pm), B, S, 592, _stream()), "mv_prep_input")
     return img, pm
 
 
@@ -208,7 +225,8 @@ def prep_input_u8(tiles, img=None, pm=None, mean=HOPTIMUS_MEAN, std=HOPTIMUS_STD
         pm = torch.empty((B * g * g, 592), dtype=torch.bfloat16, device=tiles.device)
     sc = (ctypes.c_float * 3)(*[1.0 / (255.0 * s) for s in std])
     bi = (ctypes.c_float * 3)(*[-m / s for m, s in zip(mean, std)])
-    _lib.check(lib.mv_prep_input_u8(_ptr(tiles), sc, bi, _ptr(img), _ptr(pm), B, S, 592, _stream()), "mv_prep_input_u8")
+    f16 = 1 if (img is not None and img.dtype == torch.float16) else 0
+    _lib.check(lib.mv_prep_input_u8(_ptr(tiles), sc, bi, _ptr(img), f16, _ptr(pm), B, S, 592, _stream()), "mv_prep_input_u8")
     return img, pm
 
 
@@ -224,20 +242,23 @@ def tokens_to_map(tokens, batch, n_tok, prefix, grid, target, out=None):
     lib = _lib_for(tokens)
     D = tokens.shape[1]
     if out is None:
-        out = torch.empty((batch, target, target, D), dtype=torch.bfloat16, device=tokens.device)
+        out = torch.empty((batch, target, target, D), dtype=tokens.dtype, device=tokens.device)
+    assert tokens.dtype in _H16 and out.dtype == tokens.dtype
     _lib.check(lib.mv_tokens_to_map(_ptr(tokens), tokens.stride(0), _ptr(out), batch, n_tok, prefix, grid, target, D,
-                                    _stream()), "mv_tokens_to_map")
+                                    1 if tokens.dtype == torch.float16 else 0, _stream()), "mv_tokens_to_map")
     return out
 
 
 def upsample2x(x, out=None):
     """bilinear x2, NHWC bf16 (mv_upsample2x)."""
     lib = _lib_for(x)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    assert x.dtype in _H16 and x.is_contiguous() and x.dim() == 4
     B, h, w, C = x.shape
     if out is None:
-        out = torch.empty((B, 2 * h, 2 * w, C), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.mv_upsample2x(_ptr(x), _ptr(out), B, h, w, C, _stream()), "mv_upsample2x")
+        out = torch.empty((B, 2 * h, 2 * w, C), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype
+    _lib.check(lib.mv_upsample2x(_ptr(x), _ptr(out), B, h, w, C, 1 if x.dtype == torch.float16 else 0, _stream()),
+               "mv_upsample2x")
     return out
 
 
@@ -329,37 +350,100 @@ def bn_finalize(colstats, count, gamma, beta, running_mean, running_var, pre_bia
     C = gamma.numel()
     if out is None:
         out = torch.empty((4, C), dtype=torch.float32, device=colstats.device)
+    for t in (colstats, gamma, beta, running_mean, running_var, pre_bias, out):  # raw pointers below: fp32, dense, same device
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.device == colstats.device)
     _lib.check(lib.mv_bn_finalize(_ptr(colstats), float(count), _ptr(gamma), _ptr(beta), _ptr(pre_bias), _ptr(running_mean),
                                   _ptr(running_var), float(momentum), float(eps), C, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
                                   _ptr(out[3]), _stream()), "mv_bn_finalize")
     return out
 
 
-def gram32(f, out=None):
+def gram32(f, out=None, zero=True):
     """out (fp32 [40, 32], zeroed here): rows 0..31 = f^T f, row 32 = 1^T f for f bf16 [M, 32] (mv_gram32)."""
     lib = _lib_for(f)
     _rowmajor(f, "f")
-    assert f.dtype == torch.bfloat16 and f.shape[1] == 32
+    assert f.dtype in _H16 and f.shape[1] == 32
     if out is None:
         out = torch.zeros((40, 32), dtype=torch.float32, device=f.device)
-    else:
+    elif zero:
         out.zero_()
-    _lib.check(lib.mv_gram32(_ptr(f), f.stride(0), f.shape[0], _ptr(out), _stream()), "mv_gram32")
+    _lib.check(lib.mv_gram32(_ptr(f), f.stride(0), f.shape[0], 1 if f.dtype == torch.float16 else 0, _ptr(out), _stream()),
+               "mv_gram32")
     return out
 
 
-def heads_bn_from_gram(gram, count, w1, b1, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, out=None):
+def heads_bn_from_gram(gram, count, w1, b1, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, out=None,
+                       w1_fmt=0):
     """closed-form BatchNorm batch statistics of W1 f + b1 from the moments of f (mv_heads_bn_from_gram)."""
     lib = _lib_for(gram)
     C = gamma.numel()
     assert w1.dtype == torch.float32 and w1.is_contiguous() and w1.shape == (C, 32)
+    for t in (gram, b1, gamma, beta, running_mean, running_var):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.device == gram.device)
     if out is None:
         out = torch.empty((4, C), dtype=torch.float32, device=gram.device)
     _lib.check(lib.mv_heads_bn_from_gram(_ptr(gram), float(count), _ptr(w1), _ptr(b1), _ptr(gamma), _ptr(beta),
                                          _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), C,
-                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
+                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), int(w1_fmt), _stream()),
                "mv_heads_bn_from_gram")
     return out
+
+
+def heads_bwd_algebra(E, FF, w1, b1, gamma, w2, fin, count, n_units, dw1, dgamma, dbeta, dw2, ca_t, mx_n, kshift):
+    """closed-form gate-MLP / BatchNorm backward of the 16 heads (mv_heads_bwd_algebra)."""
+    lib = _lib_for(E)
+    for t in (E, FF, w1, b1, gamma, w2, fin, dw1, dgamma, dbeta, dw2, kshift):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert E.shape == (40, 256) and FF.shape == (40, 32) and fin.shape == (4, 256) and w1.shape == (256, 32)
+    assert ca_t.dtype == torch.bfloat16 and ca_t.shape == (32, 256) and ca_t.is_contiguous()
+    assert mx_n.dtype in _H16 and mx_n.shape == (32, 64) and mx_n.is_contiguous()
+    _lib.check(lib.mv_heads_bwd_algebra(_ptr(E), _ptr(FF), _ptr(w1), _ptr(b1), _ptr(gamma), _ptr(w2), _ptr(fin), float(count),
+                                        int(n_units), _ptr(dw1), _ptr(dgamma), _ptr(dbeta), _ptr(dw2), _ptr(ca_t), _ptr(mx_n),
+                                        1 if mx_n.dtype == torch.float16 else 0, _ptr(kshift), _stream()),
+               "mv_heads_bwd_algebra")
+
+
+def lora_refresh(lora_flat, ptrs, depth, D, alpha, ldw, ldb):
+    lib = _lib_for(lora_flat)
+    assert lora_flat.dtype == torch.float32 and lora_flat.is_contiguous() and lora_flat.numel() >= depth * 32 * D
+    assert ptrs.dtype == torch.int64 and ptrs.is_contiguous() and ptrs.numel() == depth * 4
+    _lib.check(lib.mv_lora_refresh(_ptr(lora_flat), _ptr(ptrs), depth, D, float(alpha), int(ldw), int(ldb), _stream()),
+               "mv_lora_refresh")
+
+
+def gather_cast(src, idx, dst):
+    """dst[i] = convert(src[idx[i]]) (idx -1 -> 0, -2 -> untouched); dst fp32 / bf16 / fp16 (mv_gather_cast)."""
+    lib = _lib_for(src)
+    assert src.dtype == torch.float32 and src.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert dst.is_contiguous() and dst.numel() == idx.numel()
+    mode = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dst.dtype]
+    _lib.check(lib.mv_gather_cast(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), mode, _stream()), "mv_gather_cast")
+
+
+def add_i64(t, inc=1):
+    lib = _lib_for(t)
+    assert t.dtype == torch.int64 and t.is_contiguous()
+    _lib.check(lib.mv_add_i64(_ptr(t), t.numel(), int(inc), _stream()), "mv_add_i64")
+
+
+def memset(t, value=0):
+    lib = _lib_for(t)
+    assert t.is_contiguous()
+    _lib.check(lib.mv_memset_async(_ptr(t), int(value), t.numel() * t.element_size(), _stream()), "mv_memset_async")
+
+
+def adam_schedule(step, base_lr, total_steps, warmup_steps, beta1, beta2, hyper):
+    lib = _lib_for(step)
+    assert step.dtype == torch.int64 and hyper.dtype == torch.float32 and hyper.numel() >= 4
+    _lib.check(lib.mv_adam_schedule(_ptr(step), float(base_lr), int(total_steps), int(warmup_steps), float(beta1),
+                                    float(beta2), _ptr(hyper), _stream()), "mv_adam_schedule")
+
+
+def adam_clip_step_dev(params, grads, exp_avg, exp_avg_sq, norm_coef, hyper, beta1=0.5, beta2=0.999, eps=1e-7, grad_mul=1.0):
+    lib = _lib_for(params)
+    _lib.check(lib.mv_adam_clip_step_dev(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                         _ptr(norm_coef), float(grad_mul), _ptr(hyper), float(beta1), float(beta2),
+                                         float(eps), _stream()), "mv_adam_clip_step_dev")
 
 
 def bn_relu_apply(z, scale, shift, out=None):
@@ -368,8 +452,9 @@ def bn_relu_apply(z, scale, shift, out=None):
     assert z.is_contiguous()
     if out is None:
         out = torch.empty((M, C), dtype=torch.bfloat16, device=z.device)
-    _lib.check(lib.mv_bn_relu_apply(_ptr(z), 1 if z.dtype == torch.float32 else 0, _ptr(scale), _ptr(shift), _ptr(out), M, C,
-                                    _stream()), "mv_bn_relu_apply")
+    assert out.dtype in _H16 and out.is_contiguous()
+    _lib.check(lib.mv_bn_relu_apply(_ptr(z), 1 if z.dtype == torch.float32 else 0, _ptr(scale), _ptr(shift), _ptr(out),
+                                    1 if out.dtype == torch.float16 else 0, M, C, _stream()), "mv_bn_relu_apply")
     return out
 
 
@@ -394,9 +479,11 @@ def transpose_bf16(x, ones_row=False, out=None):
     ld = (M + 7) // 8 * 8
     rows = C + (8 if ones_row else 0)
     if out is None:
-        out = torch.zeros((rows, ld), dtype=torch.bfloat16, device=x.device) if ones_row else \
-            torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.mv_transpose_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, C, 1 if ones_row else 0, _stream()),
+        out = torch.zeros((rows, ld), dtype=x.dtype, device=x.device) if ones_row else \
+            torch.empty((rows, ld), dtype=x.dtype, device=x.device)
+    assert x.dtype in _H16 and out.dtype == x.dtype
+    ones = 0 if not ones_row else (2 if x.dtype == torch.float16 else 1)
+    _lib.check(lib.mv_transpose_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, C, ones, _stream()),
                "mv_transpose_bf16")
     return out
 

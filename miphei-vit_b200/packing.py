@@ -10,7 +10,19 @@ def _pad64(c):
     return (c + 63) // 64 * 64
 
 
-def pack_conv3x3(weight, splits):
+def decoder_layout(model):
+    """[(name, parameter, offset, numel)] of the trainable decoder parameters inside a flat fp32 buffer — module order,
+    every segment 16-byte aligned — and the padded total.  Shared by trainer.FlatParams (the decoder segment comes first in
+    its flat buffer) and decoder_train.DecoderTrain (gather tables), so both always agree on the offsets."""
+    out, off = [], 0
+    for n, p in model.named_parameters():
+        if n.startswith("decoder.") and p.requires_grad:
+            out.append((n, p, off, p.numel()))
+            off += (p.numel() + 3) // 4 * 4
+    return out, off
+
+
+def pack_conv3x3(weight, splits, dtype=torch.bfloat16):
     """[Cout, sum(splits), 3, 3] -> bf16 [Cout, 9 * sum(pad64(s))]: per tap (ky, kx) each source's channels zero-padded
     to a multiple of 64, sources in concat order (mv_gemm_bf16 conv mode). `splits` may hold a narrower real channel count
     than the NHWC buffer carries (e.g. the 3 image channels stored in 8): only the real channels get weights."""
@@ -24,7 +36,8 @@ def pack_conv3x3(weight, splits):
         blk[:, :, :s] = w[:, :, off:off + s]
         parts.append(blk)
         off += s
-    return torch.cat(parts, dim=2).reshape(cout, -1).to(torch.bfloat16).contiguous()
+    out = torch.cat(parts, dim=2).reshape(cout, -1)
+    return (out if dtype is None else out.to(dtype)).contiguous()
 
 
 def fold_bn_eval(bn_weight, bn_bias, running_mean, running_var, eps=1e-5, conv_bias=None):

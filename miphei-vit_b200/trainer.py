@@ -46,6 +46,9 @@ class FlatParams:
         self.total = self.n_dec + sum(pad(p.numel()) for _, p in lora)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        from .packing import decoder_layout
+        lay, n_dec = decoder_layout(model)
+        assert n_dec == self.n_dec and [n for n, _, _, _ in lay] == [n for n, _ in dec]
         off = 0
         with torch.no_grad():
             for _, p in self.order:
@@ -69,8 +72,18 @@ class FlatParams:
 
 
 class Trainer:
+    """step(x, y) = the reference's manual-optimisation training_step on the fused kernels.
+
+    Fast path (default): the step does not go through autograd at all — forward, loss, backward, clip and Adam are a fixed
+    kernel sequence over persistent buffers, captured once per batch size in CUDA graphs and replayed (no framework op and
+    no launch gap inside a step; learning rate and step count live on the device, mv_adam_schedule).  With several ranks the
+    sequence is cut into four graphs around the NCCL calls: [forward + decoder backward] -> all-reduce(decoder bucket)
+    overlapping [encoder backward, upper half] -> all-reduce(LoRA, upper blocks) overlapping [encoder backward, lower half]
+    -> all-reduce(LoRA, lower blocks) -> [clip + Adam].  step_autograd() is the same step through `model(x)` /
+    `pred.backward()` (the drop-in route a LightningModule takes)."""
+
     def __init__(self, model, marker_weights=None, base_lr=None, batch_size=None, total_steps=10000, warmup_steps=400,
-                 lambda_factor=50.0, loss_mode=ops.LOSS_WMSE, betas=(0.5, 0.999), eps=1e-7, max_norm=1.0):
+                 lambda_factor=50.0, loss_mode=ops.LOSS_WMSE, betas=(0.5, 0.999), eps=1e-7, max_norm=1.0, use_graph=True):
         self.model = model
         self.eng = model.engine
         dev = next(model.parameters()).device
@@ -91,11 +104,22 @@ class Trainer:
         self.norm = torch.zeros(2, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)   # optimiser steps taken (device copy of step_count)
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)    # written by mv_adam_schedule
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._dec_work = None
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._io = {}
         self.eng.on_encoder_backward_start = self._decoder_grads_ready
         self.eng.invalidate()
         self.eng.direct_grad_sink = True
+        self.eng.flat_params = (self.flat, self.gflat, self.n_dec)
+        # the LoRA segment must be laid out block by block as (A_q, B_q, A_v, B_v): mv_lora_refresh reads it that way
+        names = [n for n, _ in self.order if not n.startswith("decoder.")]
+        for i in range(len(names) // 4):
+            want = ["encoder.vit.blocks.%d.attn.qkv.%s" % (i, t) for t in ("lora_q.A", "lora_q.B", "lora_v.A", "lora_v.B")]
+            assert names[4 * i:4 * i + 4] == want, names[4 * i:4 * i + 4]
 
     # called by the encoder's autograd node when it starts its backward: every decoder gradient is final
     def _decoder_grads_ready(self):
@@ -108,8 +132,9 @@ class Trainer:
     def current_lr(self):
         return self.base_lr * lr_lambda(self.step_count, self.total_steps, self.warmup_steps)
 
-    def step(self, x, y):
-        """One optimisation step on device tensors x [B,3,S,S], y [B,C,S,S]; returns the loss tensor (no host sync)."""
+    # ------------------------------------------------------------------ the step through autograd (drop-in route)
+    def step_autograd(self, x, y):
+        """One optimisation step on device tensors x [B,3,S,S], y [B,C,S,S] through model(x) / backward()."""
         self.model.train()
         pred = self.model(x)
         p32 = pred.detach().float().contiguous()
@@ -122,15 +147,130 @@ class Trainer:
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
                 self._dec_work = None
             self.fp.allreduce_bucket(1, async_op=False)
+        self._optimizer_stage()
+        self._after_step()
+        return loss
+
+    def _optimizer_stage(self):
         ops.grad_norm(self.gflat, self.max_norm, norm_out=self.norm, workspace=self.norm_ws)
+        ops.adam_schedule(self.step_dev, self.base_lr, self.total_steps, self.warmup_steps, self.betas[0], self.betas[1],
+                          self.hyper)
+        ops.adam_clip_step_dev(self.flat, self.gflat, self.m, self.v, self.norm, self.hyper, self.betas[0], self.betas[1],
+                               self.eps)
+
+    def _after_step(self):
         self.step_count += 1
-        lr = self.base_lr * lr_lambda(self.step_count - 1, self.total_steps, self.warmup_steps)
-        ops.adam_clip_step(self.flat, self.gflat, self.m, self.v, self.norm, self.step_count, lr, self.betas[0],
-                           self.betas[1], self.eps)
         # parameters changed in place through the flat buffer, behind autograd's version counters
         self.eng.bump_weights()
-        self.eng._lora_bwd_versions = None
-        return loss
+
+    # ------------------------------------------------------------------ the fast path
+    def _buffers(self, B):
+        io = self._io.get(B)
+        if io is None:
+            eng = self.eng
+            shp = (B, eng.heads_out, eng.S, eng.S)
+            io = dict(y=torch.empty(shp, dtype=torch.float32, device=self.device),
+                      dpred=torch.empty(shp, dtype=torch.float32, device=self.device),
+                      loss_ws=torch.empty(int(ops._lib.load().mv_loss_workspace_floats(B, eng.heads_out, eng.S * eng.S)),
+                                          dtype=torch.float32, device=self.device))
+            self._io[B] = io
+        return io
+
+    def _stage_forward(self, tape, io):
+        """operand refresh from the flat parameters, forward, loss + its gradient, decoder backward."""
+        from .autograd import encoder_forward_train
+        eng = self.eng
+        eng.refresh_lora_operands()
+        dt = eng.decoder_train
+        dt.pack()
+        tape.generation += 1
+        fmap = encoder_forward_train(eng, tape)
+        pred = dt.forward(fmap, tape.img)
+        ops.loss_fwd_bwd(pred, io["y"], self.marker_weights, mode=self.loss_mode, lambda_factor=self.lambda_factor,
+                         grad=io["dpred"], loss=self.loss_buf, workspace=io["loss_ws"])
+        io["dfmap"] = dt.backward(io["dpred"])
+
+    def _stage_encoder_bwd(self, tape, io, hi, lo, head):
+        from .autograd import encoder_backward_blocks, encoder_backward_head
+        eng = self.eng
+        if head:
+            encoder_backward_head(eng, tape, io["dfmap"])
+        encoder_backward_blocks(eng, tape, hi, lo, lambda i: tuple(t.grad for l in eng.blocks[i]["lora"] for t in (l.A, l.B)))
+
+    def _lora_slice(self, lo, hi):
+        per = 32 * self.eng.D
+        return self.gflat[self.n_dec + lo * per:self.n_dec + hi * per]
+
+    def _allreduce(self, t):
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(self.world)
+        return None
+
+    def _stages(self, tape, io):
+        """[(callable, collective slice issued after it or None)]: one stage on a single GPU, four around the collectives."""
+        L = self.eng.depth
+        if self.world == 1:
+            def whole():
+                self._stage_forward(tape, io)
+                self._stage_encoder_bwd(tape, io, L, 0, True)
+                self._optimizer_stage()
+            return [(whole, None)]
+        half = L // 2
+        return [(lambda: self._stage_forward(tape, io), self.gflat[:self.n_dec]),
+                (lambda: self._stage_encoder_bwd(tape, io, L, half, True), self._lora_slice(half, L)),
+                (lambda: self._stage_encoder_bwd(tape, io, half, 0, False), self._lora_slice(0, half)),
+                (self._optimizer_stage, None)]
+
+    def step(self, x, y):
+        """One optimisation step; x [B,3,S,S] fp32, y [B,C,S,S] fp32 — device tensors or PINNED host tensors (copied with
+        non-blocking H2D copies).  Returns the loss as a 1-element device tensor (a persistent buffer: read it before the
+        next step); no host synchronisation."""
+        from .autograd import prepare_training
+        eng = self.eng
+        self.model.train()
+        if not eng._packed or not eng._bwd_packed or eng.decoder_train is None:
+            eng._ensure_packed(train=True)
+            prepare_training(eng)
+        eng._check_input_shape(x)
+        B = x.shape[0]
+        tape = eng._train_tape(B)
+        io = self._buffers(B)
+        tape.x_in.copy_(x, non_blocking=True)
+        io["y"].copy_(y, non_blocking=True)
+        stages = self._stages(tape, io)
+        graphs = self._graphs.get(B) if self.use_graph else None
+        if self.use_graph and graphs is None:
+            # first step at this batch size runs eagerly (buffer allocation, descriptor creation, kernel attributes);
+            # the second one is captured
+            if io.get("warm"):
+                graphs = [None] * len(stages)
+                self._graphs[B] = graphs
+            io["warm"] = True
+        cur = torch.cuda.current_stream() if self.world > 1 else None
+        works = []
+        for k, (fn, coll) in enumerate(stages):
+            if k == len(stages) - 1 and works:  # optimiser stage: every bucket reduced
+                for w in works:
+                    if w is not None:
+                        w.wait()
+                cur.wait_stream(self.comm_stream)
+            if graphs is None:
+                fn()
+            else:
+                if graphs[k] is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn()
+                    graphs[k] = g  # capture records, the replay below executes
+                graphs[k].replay()
+            if coll is not None:
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    works.append(self._allreduce(coll))
+        self._after_step()
+        return self.loss_buf
 
 
 def bench_train(model, args, rank, world, dev):

@@ -25,12 +25,12 @@ tr = Trainer(m, marker_weights=g["marker_weights"], base_lr=g["base_lr"], total_
 tr.gflat.zero_()
 # hook the feature gradient
 import miphei_vit_b200.autograd as ag
-orig = ag.encoder_backward
+orig = ag.encoder_backward_head
 cap = {}
-def wrapped(eng, tape, dmap, on_start=None):
+def wrapped(eng, tape, dmap):
     cap["dmap"] = dmap.float().cpu().clone()
-    return orig(eng, tape, dmap, on_start)
-ag.encoder_backward = wrapped
+    return orig(eng, tape, dmap)
+ag.encoder_backward_head = wrapped
 pred = m(x.cuda())
 loss, dpred = ops.loss_fwd_bwd(pred.detach().float().contiguous(), y.cuda(), tr.marker_weights, lambda_factor=50.0)
 pred.backward(dpred.to(pred.dtype))
