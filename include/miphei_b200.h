@@ -296,12 +296,20 @@ int mv_heads_bwd_stencil(const void* t, const void* ds, const void* gate, void* 
  *                       counts [batch, cap], n_unique [batch]; rows >= n_unique[b] are untouched. cap = power of two
  *                       >= the number of nuclei of any image; *overflow is set to 1 if an image has more (the caller
  *                       must pre-zero it and re-run with a larger cap).  target / means_target may both be NULL.
+ *                       The tables live in shared memory while cap * (2 chans + 10) * 4 bytes fit in 220 KB; beyond that
+ *                       (thousands of nuclei in one tile) pass a global workspace of mv_cell_means_workspace_bytes().
+ *   mv_cell_means_bwd   the extractor is differentiable in the reference (training_step's cell loss, src/models.py:
+ *                       120-131): d map[b, c, p] = d means[row(b, label p), c] / count[row], 0 on background; ids / counts /
+ *                       n_unique are the packed forward outputs.
  *   mv_cell_means_pack  concatenates the per-image rows in batch order (the reference's torch.cat): out_* hold
  *                       sum(n_unique) rows.
  * ---------------------------------------------------------------------------------------------------------- */
 int mv_cell_means(const float* pred, const float* target, const void* nuclei, int label_bytes, int batch, int chans, int hw,
                   int cap, float* means_pred, float* means_target, int64_t* ids, float* counts, int32_t* n_unique,
-                  int32_t* overflow, void* stream);
+                  int32_t* overflow, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mv_cell_means_workspace_bytes(int batch, int chans, int cap);
+int mv_cell_means_bwd(const float* dmeans, const int64_t* ids, const float* counts, const int32_t* n_unique,
+                      const void* nuclei, int label_bytes, int batch, int chans, int hw, float* dmap, void* stream);
 int mv_cell_means_pack(const float* means_pred, const float* means_target, const int64_t* ids, const float* counts,
                        const int32_t* n_unique, int batch, int chans, int cap, float* out_pred, float* out_target,
                        int64_t* out_ids, float* out_counts, void* stream);

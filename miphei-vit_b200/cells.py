@@ -10,6 +10,34 @@ import torch.nn.functional as F
 from . import ops
 
 
+class _CellMeans(torch.autograd.Function):
+    """(pred, target, nuclei) -> (pred_means, target_means, ids); differentiable in pred and target like the reference's
+    scatter_add_ formulation (the cell loss of training_step back-propagates through it, src/models.py:120-131)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, nuclei):
+        pm, tm, ids, nu, cnt = ops.cell_means(pred.float().contiguous(), target.float().contiguous(), nuclei,
+                                              return_counts=True)
+        ctx.save_for_backward(ids, cnt, nu, nuclei)
+        ctx.shape, ctx.dtypes = pred.shape, (pred.dtype, target.dtype)
+        ids_out = ids.to(nuclei.dtype)
+        ctx.mark_non_differentiable(ids_out)
+        return pm.to(pred.dtype), tm.to(pred.dtype), ids_out
+
+    @staticmethod
+    def backward(ctx, dpm, dtm, _dids):
+        ids, cnt, nu, nuclei = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        gp = gt = None
+        if ctx.needs_input_grad[0] and dpm is not None:
+            gp = (ops.cell_means_bwd(dpm, ids, cnt, nu, nuclei, B, C, H, W) if ids.numel() else
+                  torch.zeros(ctx.shape, device=dpm.device)).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1] and dtm is not None:
+            gt = (ops.cell_means_bwd(dtm, ids, cnt, nu, nuclei, B, C, H, W) if ids.numel() else
+                  torch.zeros(ctx.shape, device=dtm.device)).to(ctx.dtypes[1])
+        return gp, gt, None
+
+
 class MeanCellExtrator(nn.Module):
     def __init__(self, scale_factor=1.):
         super().__init__()
@@ -18,17 +46,14 @@ class MeanCellExtrator(nn.Module):
         self.scale_factor = scale_factor
 
     def forward(self, pred, target, nuclei):
-        if target is None:
-            target = torch.zeros_like(pred)
-        if nuclei.ndim == 3:
-            nuclei = torch.unsqueeze(nuclei, dim=1).long()
-        if self.scale_factor < 1.:
-            pred = F.interpolate(pred, scale_factor=self.scale_factor, mode='area')
-            target = F.interpolate(target, scale_factor=self.scale_factor, mode='area')
-            nuclei = F.interpolate(nuclei.float(), scale_factor=self.scale_factor, mode='nearest-exact').long()
-        return self.extract_mean(pred, target, nuclei)
+        """pred / target [B, C, H, W], nuclei [B, H, W] or [B, 1, H, W] integer labels (0 = background)."""
+        labels = nuclei[:, None].long() if nuclei.ndim == 3 else nuclei
+        target = pred.new_zeros(pred.shape) if target is None else target
+        sf = self.scale_factor
+        if sf < 1.:  # the reference shrinks maps by area averaging and the label map by exact nearest sampling first
+            pred, target = (F.interpolate(t, scale_factor=sf, mode="area") for t in (pred, target))
+            labels = F.interpolate(labels.float(), scale_factor=sf, mode="nearest-exact").long()
+        return self.extract_mean(pred, target, labels)
 
     def extract_mean(self, pred, target, nuclei):
-        dt = pred.dtype
-        pm, tm, ids, _ = ops.cell_means(pred.float().contiguous(), target.float().contiguous(), nuclei)
-        return pm.to(dt), tm.to(dt), ids.to(nuclei.dtype)
+        return _CellMeans.apply(pred, target, nuclei)

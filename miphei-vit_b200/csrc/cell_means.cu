@@ -24,11 +24,15 @@ __global__ void __launch_bounds__(CM_THREADS) cell_means_kernel(const float* __r
                                                                 const LabelT* __restrict__ nuclei, int C, int HW, int cap,
                                                                 float* __restrict__ means_pred, float* __restrict__ means_target,
                                                                 long long* __restrict__ ids, float* __restrict__ counts,
-                                                                int* __restrict__ n_unique, int* __restrict__ overflow) {
+                                                                int* __restrict__ n_unique, int* __restrict__ overflow,
+                                                                uint8_t* __restrict__ gws, long long gws_stride) {
   griddep_sync();
   extern __shared__ __align__(16) uint8_t cm_smem[];
   const int hslots = 2 * cap;  // power of two
-  long long* keys = reinterpret_cast<long long*>(cm_smem);             // [hslots] 0 = empty
+  // tables and accumulators: shared memory when they fit (the fast path), else this image's slice of a caller-provided
+  // global workspace (images with thousands of nuclei: same algorithm, the atomics go to L2)
+  uint8_t* base = gws ? gws + (long long)blockIdx.x * gws_stride : cm_smem;
+  long long* keys = reinterpret_cast<long long*>(base);                 // [hslots] 0 = empty
   long long* skey = keys + hslots;                                      // [cap] sort keys
   int* dense = reinterpret_cast<int*>(skey + cap);                      // [hslots] slot -> rank
   int* sslot = dense + hslots;                                          // [cap] sort payload (hash slot)
@@ -205,34 +209,71 @@ __global__ void cell_means_pack_kernel(const float* __restrict__ means_pred, con
 static size_t cm_smem_bytes(int C, int cap) {
   return (size_t)(2 * cap) * 8 + (size_t)cap * 8 + (size_t)(2 * cap) * 4 + (size_t)cap * 4 + (size_t)cap * (2 * C + 1) * 4;
 }
+constexpr size_t CM_SMEM_MAX = 220 * 1024;
+
+// Backward of the per-nucleus means: d pred[b, c, p] = d means[row(b, label p), c] / count[row] for labelled pixels, 0 on
+// background. ids / counts / n_unique are the forward's packed outputs (ids ascending per image): one binary search per pixel.
+template <typename LabelT>
+__global__ void cell_means_bwd_kernel(const float* __restrict__ dmeans, const long long* __restrict__ ids,
+                                      const float* __restrict__ counts, const int* __restrict__ n_unique,
+                                      const LabelT* __restrict__ nuclei, int B, int C, int HW, float* __restrict__ dmap) {
+  griddep_sync();
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  long long off = 0;
+  for (int i = 0; i < b; ++i) off += n_unique[i];
+  const int U = n_unique[b];
+  const long long k = (long long)nuclei[(long long)b * HW + p];
+  long long row = -1;
+  if (k > 0 && U > 0) {
+    int lo = 0, hi = U - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (ids[off + mid] < k) lo = mid + 1; else hi = mid;
+    }
+    if (ids[off + lo] == k) row = off + lo;
+  }
+  const float inv = row >= 0 ? 1.f / counts[row] : 0.f;
+  float* o = dmap + (long long)b * C * HW + p;
+  for (int c = 0; c < C; ++c) o[(long long)c * HW] = row >= 0 ? dmeans[row * C + c] * inv : 0.f;
+}
 
 }  // namespace mv
 
 extern "C" int mv_cell_means(const float* pred, const float* target, const void* nuclei, int label_bytes, int batch, int chans,
                              int hw, int cap, float* means_pred, float* means_target, int64_t* ids, float* counts,
-                             int32_t* n_unique, int32_t* overflow, void* stream_) {
+                             int32_t* n_unique, int32_t* overflow, void* workspace, int64_t workspace_bytes, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(pred && nuclei && means_pred && ids && counts && n_unique && overflow && batch > 0 && chans > 0 && hw > 0,
                "mv_cell_means: null/empty");
   MV_CHECK_ARG(label_bytes == 4 || label_bytes == 8, "mv_cell_means: labels must be int32 or int64");
   MV_CHECK_ARG(cap >= 32 && (cap & (cap - 1)) == 0, "mv_cell_means: cap must be a power of two >= 32 (got %d)", cap);
   MV_CHECK_ARG((target == nullptr) == (means_target == nullptr), "mv_cell_means: target and means_target go together");
-  const size_t smem = cm_smem_bytes(chans, cap);
-  MV_CHECK_ARG(smem <= 220 * 1024, "mv_cell_means: cap %d x %d channels needs %zu bytes of shared memory (max 220 KB)", cap,
-               chans, smem);
+  size_t smem = cm_smem_bytes(chans, cap);
+  const long long stride = (long long)((smem + 255) / 256 * 256);
+  uint8_t* gws = nullptr;
+  if (smem > CM_SMEM_MAX) {  // tables in global memory
+    MV_CHECK_ARG(workspace && workspace_bytes >= stride * batch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                 "mv_cell_means: cap %d x %d channels exceeds shared memory: pass a 256-byte aligned workspace of "
+                 "mv_cell_means_workspace_bytes() = %lld bytes", cap, chans, stride * batch);
+    gws = reinterpret_cast<uint8_t*>(workspace);
+    smem = 0;
+  }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   cudaError_t e = cudaSuccess;
   if (label_bytes == 4) {
     e = cudaFuncSetAttribute(cell_means_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       MV_LAUNCH(cell_means_kernel<int32_t>, batch, CM_THREADS, smem, stream, pred, target, reinterpret_cast<const int32_t*>(nuclei),
-                chans, hw, cap, means_pred, means_target, reinterpret_cast<long long*>(ids), counts, n_unique, overflow);
+                chans, hw, cap, means_pred, means_target, reinterpret_cast<long long*>(ids), counts, n_unique, overflow, gws,
+                stride);
   } else {
     e = cudaFuncSetAttribute(cell_means_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       MV_LAUNCH(cell_means_kernel<long long>, batch, CM_THREADS, smem, stream, pred, target,
                 reinterpret_cast<const long long*>(nuclei), chans, hw, cap, means_pred, means_target,
-                reinterpret_cast<long long*>(ids), counts, n_unique, overflow);
+                reinterpret_cast<long long*>(ids), counts, n_unique, overflow, gws, stride);
   }
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(cell_means): %s", cudaGetErrorString(e));
@@ -252,5 +293,30 @@ extern "C" int mv_cell_means_pack(const float* means_pred, const float* means_ta
   MV_LAUNCH(cell_means_pack_kernel, batch, 256, 0, stream, means_pred, means_target, reinterpret_cast<const long long*>(ids), counts,
             n_unique, chans, cap, out_pred, out_target, reinterpret_cast<long long*>(out_ids), out_counts);
   MV_CHECK_LAUNCH("cell_means_pack");
+  return MV_OK;
+}
+
+// bytes of global workspace mv_cell_means needs for this (batch, chans, cap); 0 when the tables fit in shared memory
+extern "C" int64_t mv_cell_means_workspace_bytes(int batch, int chans, int cap) {
+  const size_t smem = mv::cm_smem_bytes(chans, cap);
+  if (smem <= mv::CM_SMEM_MAX) return 0;
+  return (int64_t)((smem + 255) / 256 * 256) * batch;
+}
+
+extern "C" int mv_cell_means_bwd(const float* dmeans, const int64_t* ids, const float* counts, const int32_t* n_unique,
+                                 const void* nuclei, int label_bytes, int batch, int chans, int hw, float* dmap,
+                                 void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(ids && counts && n_unique && nuclei && dmap && batch > 0 && chans > 0 && hw > 0, "mv_cell_means_bwd: null/empty");
+  MV_CHECK_ARG(label_bytes == 4 || label_bytes == 8, "mv_cell_means_bwd: labels must be int32 or int64");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid((hw + 255) / 256, batch);
+  if (label_bytes == 4)
+    MV_LAUNCH(cell_means_bwd_kernel<int32_t>, grid, 256, 0, stream, dmeans, reinterpret_cast<const long long*>(ids), counts,
+              n_unique, reinterpret_cast<const int32_t*>(nuclei), batch, chans, hw, dmap);
+  else
+    MV_LAUNCH(cell_means_bwd_kernel<long long>, grid, 256, 0, stream, dmeans, reinterpret_cast<const long long*>(ids), counts,
+              n_unique, reinterpret_cast<const long long*>(nuclei), batch, chans, hw, dmap);
+  MV_CHECK_LAUNCH("cell_means_bwd");
   return MV_OK;
 }

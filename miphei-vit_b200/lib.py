@@ -95,7 +95,10 @@ _SIGNATURES = {
     "mv_heads_bwd_stencil": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p]),
     "mv_cell_means": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "mv_cell_means_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
+    "mv_cell_means_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p]),
     "mv_cell_means_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "mv_loss_workspace_floats": (c_i64, [c_int, c_int, c_int]),

@@ -564,13 +564,17 @@ def cell_means(pred, target, nuclei, cap=1024, return_counts=False):
         ids = torch.empty((B, cap), dtype=torch.int64, device=dev)
         cnt = torch.empty((B, cap), dtype=torch.float32, device=dev)
         nu = torch.zeros(B + 1, dtype=torch.int32, device=dev)  # [B] counts + overflow flag
+        wsb = int(lib.mv_cell_means_workspace_bytes(B, C, cap))  # 0 while the tables fit in shared memory
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
         _lib.check(lib.mv_cell_means(_ptr(pred), _ptr(target), _ptr(nuclei), nuclei.element_size(), B, C, H * W, cap, _ptr(mp),
-                                     _ptr(mt), _ptr(ids), _ptr(cnt), _ptr(nu), ctypes.c_void_p(nu.data_ptr() + 4 * B), _stream()),
-                   "mv_cell_means")
+                                     _ptr(mt), _ptr(ids), _ptr(cnt), _ptr(nu), ctypes.c_void_p(nu.data_ptr() + 4 * B), _ptr(ws),
+                                     wsb, _stream()), "mv_cell_means")
         host = nu.cpu()
         if int(host[B]) == 0:
             break
-        cap *= 2  # an image holds more nuclei than rows: retry with a larger table (raises when shared memory runs out)
+        if cap >= H * W:
+            raise _lib.MipheiB200Error("mv_cell_means: more distinct labels than pixels?")
+        cap *= 2  # an image holds more nuclei than rows: retry with a larger table (global-memory tables beyond ~1.3 k)
     n = int(host[:B].sum())
     op = torch.empty((n, C), dtype=torch.float32, device=dev)
     ot = torch.empty((n, C), dtype=torch.float32, device=dev) if target is not None else None
@@ -582,3 +586,17 @@ def cell_means(pred, target, nuclei, cap=1024, return_counts=False):
     if return_counts:
         return op, ot, oi, nu[:B], oc
     return op, ot, oi, nu[:B]
+
+
+def cell_means_bwd(dmeans, ids, counts, n_unique, nuclei, B, C, H, W):
+    """d map [B, C, H, W] (fp32) from d means [n, C]: mv_cell_means_bwd."""
+    lib = _lib_for(dmeans)
+    dmeans = dmeans.float().contiguous()
+    nuclei = nuclei.reshape(B, H * W)
+    if nuclei.dtype not in (torch.int32, torch.int64):
+        nuclei = nuclei.long()
+    nuclei = nuclei.contiguous()
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dmeans.device)
+    _lib.check(lib.mv_cell_means_bwd(_ptr(dmeans), _ptr(ids), _ptr(counts), _ptr(n_unique), _ptr(nuclei), nuclei.element_size(),
+                                     B, C, H * W, _ptr(out), _stream()), "mv_cell_means_bwd")
+    return out

@@ -67,3 +67,56 @@ def test_mean_cell_extrator_mirror_of_reference_class():
     assert float(tm0.abs().max()) == 0.0 and torch.allclose(pm0, pm)
     with pytest.raises(ValueError):
         MeanCellExtrator(scale_factor=1.5)
+
+
+def _torch_means(pred, nuclei):
+    """differentiable torch restatement (torch.unique + index_add per image), used only to check gradients"""
+    B, C, H, W = pred.shape
+    rows = []
+    for b in range(B):
+        lab = nuclei[b].reshape(-1)
+        keep = lab > 0
+        if not keep.any():
+            continue
+        u, inv = torch.unique(lab[keep], return_inverse=True)
+        vals = pred[b].reshape(C, -1)[:, keep].t()
+        s = torch.zeros((u.numel(), C), dtype=pred.dtype, device=pred.device).index_add(0, inv, vals)
+        n = torch.zeros(u.numel(), dtype=pred.dtype, device=pred.device).index_add(0, inv, torch.ones_like(inv, dtype=pred.dtype))
+        rows.append(s / n[:, None])
+    return torch.cat(rows)
+
+
+def test_mean_cell_extrator_is_differentiable_like_the_reference():
+    """training_step feeds the extractor's output to the cell loss (src/models.py:120-131): gradients must reach pred."""
+    from miphei_vit_b200.cells import MeanCellExtrator
+    pred, target, nuclei = _case(11, B=3, C=6, S=64, n_cells=20, empty=(1,))
+    m = MeanCellExtrator(scale_factor=1.0)
+    p = pred.cuda().requires_grad_(True)
+    t = target.cuda().requires_grad_(True)
+    pm, tm, ids = m(p, t, nuclei.cuda())
+    wgt = torch.randn(pm.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    ((pm - tm) * wgt).sum().backward()
+    pr = pred.cuda().double().requires_grad_(True)
+    ref = _torch_means(pr, nuclei.cuda())
+    (ref * wgt.double()).sum().backward()
+    assert torch.allclose(p.grad.double(), pr.grad, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(t.grad.double(), -pr.grad, rtol=1e-5, atol=1e-8)
+    assert float(p.grad[1].abs().max()) == 0.0            # empty image: no gradient
+    # half-resolution path keeps the autograd chain through F.interpolate
+    p2 = pred.cuda().requires_grad_(True)
+    pm2, _, _ = MeanCellExtrator(scale_factor=0.5)(p2, None, nuclei.cuda())
+    pm2.sum().backward()
+    assert p2.grad is not None and float(p2.grad.abs().sum()) > 0
+
+
+def test_cell_means_thousands_of_nuclei_use_the_global_workspace():
+    """more nuclei per tile than the shared-memory tables hold (the reference handles any count): 4096 labels per image"""
+    S, B, C = 256, 2, 16
+    g = torch.Generator().manual_seed(5)
+    pred, target = torch.rand((B, C, S, S), generator=g), torch.rand((B, C, S, S), generator=g)
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    lab = (yy // 4) * (S // 4) + (xx // 4) + 1          # 4096 labels of 16 pixels each
+    nuclei = torch.stack([lab, lab.flip(0) * 3])
+    nuclei[1][:8] = 0
+    gid = _check(pred, target, nuclei)
+    assert gid.numel() == 4096 + 4096 - 2 * 64
