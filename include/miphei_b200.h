@@ -112,8 +112,9 @@ typedef struct mv_gemm_args {
                          BatchNorm batch statistics of a train-mode conv; out may be NULL (statistics only) */
   int32_t kskip_begin, kskip_end; /* LINEAR: K range [begin, end) (multiples of 64) whose B columns are all zero and is
                                      not loaded at all (dT = [dQ | dK | dV] . [aB_q ; 0 ; aB_v]^T skips the dK third) */
-  int32_t ab_f16;     /* bit 0: A (and a2) hold fp16 instead of bf16, bit 1: B holds fp16 (kind::f16 takes either format
-                         per operand). The training-mode decoder keeps feature maps and conv weights in fp16: the
+  int32_t ab_f16;     /* 0: A, a2 and B hold bf16; 3: all hold fp16 (kind::f16 takes either format, but both operands must
+                         share it: a mixed descriptor is an illegal instruction on sm_100a — measured).
+                         The training-mode decoder keeps feature maps and conv weights in fp16: the
                          reference trains under fp16 autocast (configs/config.yaml:23) and the LoRA gradients need the
                          extra mantissa bits. Outputs are unaffected. */
   int32_t reserved3;
@@ -279,8 +280,12 @@ int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, i
 /* ------------------------------------------------------------------------------------------------------------
  * Memory-bound kernels of the decoder backward pass (csrc/decoder_bwd_ew.cu).
  * ---------------------------------------------------------------------------------------------------------- */
-/* 16-bit transpose; ones_row: 0 none, 1 append a row of bf16 ones, 2 a row of fp16 ones (fp16 data) */
-int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row, void* stream);
+/* [m, c] -> bf16 [c (+ a row of ones), ldo]; in_f16: the input holds fp16 and is converted on the way (the weight-gradient
+ * GEMMs pair it with bf16 gradients, and both tensor-core operands must share one format) */
+int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row, int in_f16,
+                      void* stream);
+/* dst bf16 [n] = src fp16 [n] (n % 8 == 0): bf16 twins of the fp16 activation maps for the weight-gradient GEMMs */
+int mv_f16_to_bf16(const void* src, void* dst, int64_t n, void* stream);
 int mv_upsample2x_bwd(const void* dup, int64_t ldu, void* dx, int batch, int h, int w, int c, void* stream);
 int mv_zero_insert2x(const void* dz, void* u, int batch, int h, int w, int c, void* stream);
 int mv_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t m, int c, void* stream);

@@ -14,6 +14,7 @@
 namespace mv {
 
 // in [M, C] (pitch ldi) -> out [R, ldo] with out[c, m] = in[m, c]; optional extra row C filled with ones.
+template <bool IN_F16>
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out,
                                       long long ldo, long long M, int C, int ones_row) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
@@ -25,8 +26,13 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
     const int c = c0 + threadIdx.x * 2;
     __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
     if (m < M && c < C) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(in + m * ldi + c);
-      a = v.x; b = v.y;
+      if (IN_F16) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(in + m * ldi + c));
+        a = __float2bfloat16(f.x); b = __float2bfloat16(f.y);
+      } else {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(in + m * ldi + c);
+        a = v.x; b = v.y;
+      }
     }
     tile[i][threadIdx.x * 2] = a;
     tile[i][threadIdx.x * 2 + 1] = b;
@@ -44,10 +50,9 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
     }
   }
   if (ones_row && blockIdx.y == 0) {
-    // ones_row: 1 = bf16 data, 2 = fp16 data (the kernel only moves 16-bit words; the constant must match the format)
-    const unsigned short one = ones_row == 2 ? 0x3C00u : 0x3F80u;
+    const __nv_bfloat16 one = __float2bfloat16(1.f);
     for (int i = threadIdx.y * 32 + threadIdx.x; i < 64; i += 32 * blockDim.y)
-      if (m0 + i < M) reinterpret_cast<unsigned short*>(out)[(long long)C * ldo + m0 + i] = one;
+      if (m0 + i < M) out[(long long)C * ldo + m0 + i] = one;
   }
 }
 
@@ -256,16 +261,30 @@ __global__ void __launch_bounds__(128) heads_bwd_stencil_kernel(const __nv_bfloa
   if (threadIdx.x < 16) atomicAdd(db2 + threadIdx.x, sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
 }
 
+// bf16 twin of an fp16 tensor, 8 elements per thread
+__global__ void f16_to_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = src[i];
+    const float2 a = unpack16x2<true>(u.x), b = unpack16x2<true>(u.y), c = unpack16x2<true>(u.z), d = unpack16x2<true>(u.w);
+    dst[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y), pack_bf16x2(c.x, c.y), pack_bf16x2(d.x, d.y));
+  }
+}
+
 }  // namespace mv
 
 extern "C" int mv_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t m, int c, int ones_row,
-                                 void* stream_) {
+                                 int in_f16, void* stream_) {
   using namespace mv;
   MV_CHECK_ARG(in && out && m > 0 && c > 0 && c % 2 == 0 && ldi % 2 == 0 && ldo % 2 == 0 && ldo >= m, "mv_transpose_bf16: shape");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   dim3 grid((unsigned)((m + 63) / 64), (c + 63) / 64), block(32, 8);
-  MV_LAUNCH(transpose_bf16_kernel, grid, block, 0, stream, reinterpret_cast<const __nv_bfloat16*>(in), ldi,
-                                                    reinterpret_cast<__nv_bfloat16*>(out), ldo, m, c, ones_row);
+  if (in_f16)
+    MV_LAUNCH(transpose_bf16_kernel<true>, grid, block, 0, stream, reinterpret_cast<const __nv_bfloat16*>(in), ldi,
+              reinterpret_cast<__nv_bfloat16*>(out), ldo, (long long)m, c, ones_row);
+  else
+    MV_LAUNCH(transpose_bf16_kernel<false>, grid, block, 0, stream, reinterpret_cast<const __nv_bfloat16*>(in), ldi,
+              reinterpret_cast<__nv_bfloat16*>(out), ldo, (long long)m, c, ones_row);
   MV_CHECK_LAUNCH("transpose_bf16");
   return MV_OK;
 }
@@ -328,5 +347,19 @@ extern "C" int mv_heads_bwd_stencil(const void* t, const void* ds, const void* g
       reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<__nv_bfloat16*>(dt),
       reinterpret_cast<__nv_bfloat16*>(du), db2, h, w, M);
   MV_CHECK_LAUNCH("heads_bwd_stencil");
+  return MV_OK;
+}
+
+extern "C" int mv_f16_to_bf16(const void* src, void* dst, int64_t n, void* stream_) {
+  using namespace mv;
+  MV_CHECK_ARG(src && dst && n > 0 && n % 8 == 0, "mv_f16_to_bf16: n must be a positive multiple of 8");
+  MV_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "mv_f16_to_bf16: alignment");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)(device_sms() > 0 ? device_sms() : 148) * 16;
+  if (blocks > cap) blocks = cap;
+  MV_LAUNCH(f16_to_bf16_kernel, (unsigned)blocks, 256, 0, stream, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), n8);
+  MV_CHECK_LAUNCH("f16_to_bf16");
   return MV_OK;
 }

@@ -1090,6 +1090,8 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
   MV_CHECK_ARG(a.a && a.b && (a.out || a.colstats), "mv_gemm_bf16: null operand");
   MV_CHECK_ARG(!a.colstats || (a.mode == MV_GEMM_LINEAR && a.n >= 32), "mv_gemm_bf16: colstats needs LINEAR mode, N >= 32");
   MV_CHECK_ARG(a.m > 0 && a.n > 0 && a.k > 0, "mv_gemm_bf16: empty problem m=%d n=%d k=%d", a.m, a.n, a.k);
+  // measured on B200: a kind::f16 instruction descriptor whose A and B formats differ is an ILLEGAL INSTRUCTION
+  MV_CHECK_ARG(a.ab_f16 == 0 || a.ab_f16 == 3, "mv_gemm_bf16: A and B must share one 16-bit format (both bf16 or both fp16)");
   MV_CHECK_ARG(a.n % 8 == 0 || a.mode == MV_GEMM_HEAD_CONV, "mv_gemm_bf16: N=%d must be a multiple of 8", a.n);
   MV_CHECK_ARG(a.k % 8 == 0 || a.mode == MV_GEMM_NN_ATOMIC, "mv_gemm_bf16: K=%d must be a multiple of 8", a.k);
   MV_CHECK_ARG((a.conv || a.lda % 8 == 0) && a.ldb % 8 == 0, "mv_gemm_bf16: lda/ldb must be multiples of 8 elements");

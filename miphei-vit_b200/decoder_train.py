@@ -6,8 +6,9 @@ Precision.  Feature maps and forward conv operands are **fp16** (NHWC), raw conv
 reduction (statistics, weight gradients) fp32.  The reference trains under fp16 autocast (configs/config.yaml:23); with
 bf16 maps the LoRA gradients — a small residual of a DC-dominated decoder gradient — lose cosine 3e-3 against the fp32
 oracle through ReLU-mask / statistic perturbations of the FORWARD values (tests/tools/emulate_bf16_grads.py), with fp16
-maps 3e-4.  The tensor core takes either 16-bit format per operand (mv_gemm_args.ab_f16), so the weight-gradient GEMMs mix
-bf16 gradients with fp16 activations.
+maps 3e-4.  The tensor core takes either 16-bit format, but both operands of an instruction must share it (a mixed
+descriptor is an illegal instruction on sm_100a — measured), so the weight-gradient GEMMs, whose other operand is a bf16
+gradient, read bf16 twins of the activation maps (mv_f16_to_bf16: +4 B per element, ~0.3 % of a step).
 
 No framework ops inside a step.  All trainable decoder parameters are read from ONE flat fp32 buffer (the trainer's, or a
 private staging copy on the plain autograd path) through index tables built once: `pack()` is three table-driven launches
@@ -283,6 +284,10 @@ class DecoderTrain:
         L["z"], L["y"], L["fin"], L["M"], L["Ho"] = z, y, fin, M, Ho
         return y.view(Bn, Ho, Ho, cout)
 
+    def _twin(self, key, t):
+        """bf16 copy of an fp16 map (B operand of the weight-gradient GEMM, next to the bf16 dz^T)."""
+        return ops.f16_to_bf16(t, out=self._buf(key, tuple(t.shape), torch.bfloat16))
+
     def forward(self, fmap, img):
         """fmap NHWC fp16 [B, t, t, D], img NHWC fp16 [B, S, S, 8] -> pred fp32 NCHW [B, heads, S, S] (persistent buffer)."""
         eng = self.eng
@@ -292,15 +297,17 @@ class DecoderTrain:
         ops.memset(self.acc.data)
         ops.add_i64(self.nbt, 1)
         d = [img]
+        db = [self._twin("img.b", img)]
         for i, L in enumerate(self.cs):
-            L["srcs"] = [d[i]]
+            L["srcs"] = [db[i]]
             d.append(self._conv_bn_relu(L, d[i], None, 2, Bn, S >> (i + 1)))
+            db.append(self._twin("cs%d.yb" % i, d[-1]))
         f = fmap
         for i, L in enumerate(self.fu):
             h2 = f.shape[1] * 2
             up = self._buf("fu%d.up" % i, (Bn, h2, h2, f.shape[3]), ADT)
             ops.upsample2x(f, out=up)
-            L["srcs"] = [d[3 - i], up]
+            L["srcs"] = [db[3 - i], self._twin("fu%d.upb" % i, up)]
             f = self._conv_bn_relu(L, d[3 - i], up, 1, Bn, h2)
         M = Bn * S * S
         f2 = f.view(M, 32)
@@ -355,7 +362,7 @@ class DecoderTrain:
         du = self._buf("hd.du", (M, 16), bf)
         ops.heads_bwd_stencil(T, ds, self.gate, Bn, S, S, acc["hd.db2"], dt=dt, du=du)
         ld = (M + 7) // 8 * 8
-        fT = self._buf("hd.fT", (40, ld), ADT, zero=True)
+        fT = self._buf("hd.fT", (40, ld), bf, zero=True)   # bf16 (converted by the transpose): it meets bf16 dt / e
         ops.transpose_bf16(f2, ones_row=True, out=fT)
         fTm = fT[:, :M]
         ops.gemm(fTm, dt, mode=ops.GEMM_NN_ATOMIC, out=acc["hd.G3"])             # f^T dt

@@ -87,7 +87,8 @@ _SIGNATURES = {
     "mv_bn_relu_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p]),
     "mv_bn_relu_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_i64, c_int, c_void_p]),
-    "mv_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
+    "mv_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
+    "mv_f16_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "mv_upsample2x_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_zero_insert2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mv_add_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p]),

@@ -132,12 +132,9 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     args.block_n = block_n
     args.reserved2 = pair  # 0 auto, 1 never, 2 always: CTA-pair (cta_group::2) tiles
     a2t = conv.get("a2") if conv is not None else None
-    if conv is not None and mode == GEMM_NN_ATOMIC:  # wgrad: b (and a2) are the NHWC maps, both read as the B operand
-        assert a2t is None or a2t.dtype == b.dtype
-        args.ab_f16 = (1 if a.dtype == torch.float16 else 0) | (2 if b.dtype == torch.float16 else 0)
-    else:
-        assert a2t is None or a2t.dtype == a.dtype
-        args.ab_f16 = (1 if a.dtype == torch.float16 else 0) | (2 if b.dtype == torch.float16 else 0)
+    # both tensor-core operands must share one format (a mixed descriptor is an illegal instruction on sm_100a)
+    assert a.dtype == b.dtype and (a2t is None or a2t.dtype == a.dtype), (a.dtype, b.dtype)
+    args.ab_f16 = 3 if a.dtype == torch.float16 else 0
     if kskip is not None:  # K range with all-zero B columns: never loaded
         args.kskip_begin, args.kskip_end = int(kskip[0]), int(kskip[1])
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")
@@ -473,18 +470,29 @@ def bn_relu_bwd(dy, y, z, mean, rstd, gamma, sums=None, dz=None):
 
 
 def transpose_bf16(x, ones_row=False, out=None):
-    """[M, C] (strided rows) -> [C (+1 ones row, padded to 8 rows), ld >= M] K-major copy (mv_transpose_bf16)."""
+    """[M, C] (strided rows; bf16, or fp16 converted on the way) -> bf16 [C (+1 ones row, padded to 8 rows), ld >= M]
+    K-major copy (mv_transpose_bf16)."""
     lib = _lib_for(x)
     M, C = x.shape
     ld = (M + 7) // 8 * 8
     rows = C + (8 if ones_row else 0)
     if out is None:
-        out = torch.zeros((rows, ld), dtype=x.dtype, device=x.device) if ones_row else \
-            torch.empty((rows, ld), dtype=x.dtype, device=x.device)
-    assert x.dtype in _H16 and out.dtype == x.dtype
-    ones = 0 if not ones_row else (2 if x.dtype == torch.float16 else 1)
-    _lib.check(lib.mv_transpose_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, C, ones, _stream()),
-               "mv_transpose_bf16")
+        out = torch.zeros((rows, ld), dtype=torch.bfloat16, device=x.device) if ones_row else \
+            torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    assert x.dtype in _H16 and out.dtype == torch.bfloat16
+    _lib.check(lib.mv_transpose_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, C, 1 if ones_row else 0,
+                                     1 if x.dtype == torch.float16 else 0, _stream()), "mv_transpose_bf16")
+    return out
+
+
+def f16_to_bf16(x, out=None):
+    """bf16 twin of a contiguous fp16 tensor (mv_f16_to_bf16)."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.numel() % 8 == 0
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == x.numel()
+    _lib.check(lib.mv_f16_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "mv_f16_to_bf16")
     return out
 
 

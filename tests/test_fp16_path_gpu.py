@@ -23,28 +23,40 @@ def _rel(got, ref):
     return (got.float() - ref.float()).abs().max().item() / (ref.float().abs().max().item() + 1e-12)
 
 
-@pytest.mark.parametrize("adt,bdt", [(H, H), (H, B16), (B16, H)])
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (5264, 1536, 512), (2100, 144, 32), (700, 48, 192)])
-def test_gemm_fp16_and_mixed_operands(adt, bdt, M, N, K):
-    """kind::f16 UMMA with the A / B formats chosen per operand: fp32 output must equal the fp32 product of the ROUNDED
-    operands to accumulation-order accuracy (this is what separates a format mix-up from a rounding difference)."""
+def test_gemm_fp16_operands(M, N, K):
+    """kind::f16 UMMA with fp16 A and B: the fp32 output must equal the fp32 product of the ROUNDED operands to
+    accumulation-order accuracy (this is what separates a format mix-up from a rounding difference)."""
     ops = _ops()
-    a = _rand((M, K), 1.0, 1).to(adt)
-    b = _rand((N, K), 0.05, 2).to(bdt)
+    a = _rand((M, K), 1.0, 1).to(H)
+    b = _rand((N, K), 0.05, 2).to(H)
     out = ops.gemm(a, b, out_dtype=torch.float32)
     assert _rel(out, a.float() @ b.float().t()) < 2e-5
+    # weight-gradient form (reduction index slow in both operands, MN-major B): out[N, 64] = b^T[N, M'] . c[M', 64]
+    Mp = M // 8 * 8
+    at = a[:Mp].t().contiguous()                      # [K, Mp] used as the A operand [rows = K, reduction = Mp]
+    c = _rand((Mp, 64), 0.05, 3).to(H)
+    out2 = torch.zeros((K, 64), device="cuda")
+    ops.gemm(at, c, mode=ops.GEMM_NN_ATOMIC, out=out2)
+    assert _rel(out2, at.float() @ c.float()) < 2e-5
 
 
-@pytest.mark.parametrize("adt,bdt", [(H, B16), (B16, H), (H, H)])
-def test_gemm_nn_atomic_mixed_operands(adt, bdt):
-    """weight-gradient form (MN-major B operand) with mixed formats: f^T dt of the heads backward (fp16 x bf16)."""
+def test_mixed_operand_formats_are_rejected_on_the_host():
+    """a kind::f16 descriptor with different A / B formats is an illegal instruction on sm_100a (measured: it kills the
+    context) — the C ABI and the wrapper must refuse it before anything is launched"""
+    from miphei_vit_b200 import lib
     ops = _ops()
-    M, K, N = 40, 8192, 144
-    a = _rand((M, K), 1.0, 1).to(adt)
-    b = _rand((K, N), 0.05, 2).to(bdt)
-    out = torch.zeros((M, N), device="cuda")
-    ops.gemm(a, b, mode=ops.GEMM_NN_ATOMIC, out=out)
-    assert _rel(out, a.float() @ b.float()) < 2e-5
+    a = _rand((256, 64), 1.0, 1).to(H)
+    b = _rand((128, 64), 1.0, 2).to(B16)
+    with pytest.raises(AssertionError):
+        ops.gemm(a, b)
+    args = lib.GemmArgs()
+    out = torch.empty((256, 128), dtype=B16, device="cuda")
+    args.a, args.lda, args.b, args.ldb = a.data_ptr(), 64, b.data_ptr(), 64
+    args.m, args.n, args.k, args.out, args.ldo, args.ab_f16 = 256, 128, 64, out.data_ptr(), 128, 1
+    import ctypes
+    assert lib.init(0).mv_gemm_bf16(ctypes.byref(args), None) == -1
+    assert "share one 16-bit format" in lib.last_error()
 
 
 def test_conv_fwd_and_wgrad_fp16_maps():
@@ -69,7 +81,10 @@ def test_conv_fwd_and_wgrad_fp16_maps():
     M = dz.shape[0]
     kp = 9 * (128 + 128)
     dwp = torch.zeros((Cout, kp), device="cuda")
-    ops.gemm(dzT[:, :M], n0, mode=ops.GEMM_NN_ATOMIC, conv=dict(stride=1, a2=n1), out=dwp)
+    b0, b1 = ops.f16_to_bf16(n0), ops.f16_to_bf16(n1)   # bf16 twins: both operands of the weight-gradient GEMM are bf16
+    assert torch.equal(b0, n0.to(B16)) and b0.dtype == B16
+    xin = torch.cat([b0.float(), b1.float()], 3).permute(0, 3, 1, 2)
+    ops.gemm(dzT[:, :M], b0, mode=ops.GEMM_NN_ATOMIC, conv=dict(stride=1, a2=b1), out=dwp)
     xr = xin.clone().requires_grad_(False)
     wr = w.clone().requires_grad_(True)
     F.conv2d(xr, wr, padding=1).backward(dz.float().view(Bn, Hh, Hh, Cout).permute(0, 3, 1, 2))
@@ -123,9 +138,9 @@ def test_elementwise_fp16_variants():
     fd = f.double()
     assert torch.allclose(gram[:32].double(), fd.t() @ fd, rtol=2e-4, atol=0.1)
     assert torch.allclose(gram[32].double(), fd.sum(0), rtol=2e-4, atol=1e-2)
-    # transpose with an fp16 row of ones
+    # transpose of an fp16 map: converted to bf16 on the way (it meets bf16 gradients in the moment GEMMs), row of ones
     fT = ops.transpose_bf16(f, ones_row=True)
-    assert torch.equal(fT[:32, :5000], f.t()) and bool((fT[32, :5000] == 1).all())
+    assert fT.dtype == B16 and torch.equal(fT[:32, :5000], f.t().to(B16)) and bool((fT[32, :5000] == 1).all())
 
 
 def test_gather_cast_add_i64_memset():
