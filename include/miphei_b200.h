@@ -319,6 +319,35 @@ int mv_cell_means_pack(const float* means_pred, const float* means_target, const
                        const int32_t* n_unique, int batch, int chans, int cap, float* out_pred, float* out_target,
                        int64_t* out_ids, float* out_counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Whole-slide plumbing (csrc/wsi.cu).
+ *   mv_thumb_std_hist  get_locs_otsu (slidevips-python/slidevips/tiling.py:25-31): thumb uint8 [n_pix, chans] interleaved ->
+ *                      std_u8 [n_pix] = np.uint8(thumbnail.std(axis=-1)) bit-exactly (chans == 1: copy) and its histogram
+ *                      (uint32 [256], overwritten).
+ *   mv_otsu_threshold  the threshold cv2.threshold(src, 0, 255, THRESH_BINARY + THRESH_OTSU) selects (tiling.py:30), from the
+ *                      histogram; *thresh (device int32).
+ *   mv_tile_tissue     tiling.py:52-60: counts[i] = #{mask > threshold} in box i = (x0, y0, x1, y1) (int32 [n, 4], clipped to
+ *                      the map by the caller); threshold from thresh_dev (device, may be NULL) else fixed_thresh.
+ *   mv_stitch_tiles    preprocessings/cycle_gan/cycle_gan_wsi_inference.py:98-104: tiles uint8 [batch, chans, size, size];
+ *                      the window [crop, crop + keep)^2 of tile b goes to canvas[:, y.., x..] with (x, y) = xy[b] (int32
+ *                      [batch, 2]), clipped to the canvas uint8 [chans, canvas_h, canvas_w] (pyvips insert). The canvas may be
+ *                      device memory or mapped pinned host memory. sequential != 0 inserts tile by tile (later wins) for
+ *                      windows that overlap each other.
+ *   mv_host_alloc_mapped / mv_host_free      zeroed pinned host memory addressable by kernels (*device_ptr) — slide canvases.
+ *   mv_host_register / mv_host_unregister    page-lock an existing host range (shared-memory ring filled by loader
+ *                      worker processes, src/dataset.py:545-575 / slidevips torch_datasets.py:88-127).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mv_thumb_std_hist(const void* thumb, int64_t n_pix, int chans, void* std_u8, uint32_t* hist256, void* stream);
+int mv_otsu_threshold(const uint32_t* hist256, int64_t n_pix, int32_t* thresh, void* stream);
+int mv_tile_tissue(const void* mask_u8, int width, const int32_t* thresh_dev, int fixed_thresh, const int32_t* boxes,
+                   int n_boxes, int32_t* counts, void* stream);
+int mv_stitch_tiles(const void* tiles_u8, const int32_t* xy, int batch, int chans, int size, int crop, int keep,
+                    void* canvas_u8, int64_t canvas_h, int64_t canvas_w, int sequential, void* stream);
+int mv_host_alloc_mapped(int64_t bytes, void** host_ptr, void** device_ptr);
+int mv_host_free(void* host_ptr);
+int mv_host_register(void* ptr, int64_t bytes);
+int mv_host_unregister(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

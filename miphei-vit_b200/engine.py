@@ -331,23 +331,27 @@ class MipheiEngine:
         return gr
 
     @torch.no_grad()
-    def infer_stream(self, batches, out_dtype=torch.uint8, depth=2):
+    def infer_stream(self, batches, out_dtype=torch.uint8, depth=2, device_sink=None, to_host=True):
         """Whole-slide style inference over an iterable of PINNED host batches — fp32 NCHW normalised tiles (the
         reference's DataLoader output) or raw uint8 NHWC tiles (normalised on the device) — yielding pinned host
-        predictions [B, C, S, S] (uint8 sink of src/callbacks.py:345-346 by default, or fp32).
+        predictions [B, C, S, S] (uint8 sink of src/callbacks.py:345-346 by default, or fp32), in submission order.
 
-        Double-buffered: the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams while batch i
-        computes (one captured graph per buffer). A yielded tensor is reused `depth` batches later: consume it first."""
+        Pipelined: the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams while batch i computes
+        (one captured graph per device slot, `depth` slots).  Host output buffers rotate over depth + 2 pinned tensors
+        allocated once per engine: a yielded tensor stays valid until TWO more results have been pulled — copy it if it must
+        live longer.  device_sink(dev_out, i): called on the compute stream right after batch i (device tensor, valid only
+        inside the call) — e.g. TileStitcher.insert; with to_host=False nothing is copied back and None is yielded."""
         self._ensure_packed()
         assert out_dtype in (torch.uint8, torch.float32)
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_io_streams"):
             self._io_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._stream_bufs = {}
         s_in, s_run, s_out = self._io_streams
-        slots = {}
+        n_host = depth + 2
         pending = []  # (event, host tensor) in submission order
-        ev_free = {}  # slot -> event: its output buffer has been copied out (the slot may run again)
+        ev_free = {}  # device slot -> event: input consumed, output copied out / sunk (the slot may run again)
         i = 0
         for xb in batches:
             B = xb.shape[0]
@@ -356,17 +360,20 @@ class MipheiEngine:
                 assert xb.dim() == 4 and xb.shape[3] == 3 and xb.shape[1] == self.S and xb.shape[2] == self.S
             else:
                 self._check_input_shape(xb)
-            k = (B, i % depth)
-            if k not in slots:
-                ws = self._workspace(B, 100 + i % depth)
-                if u8_in and not hasattr(ws, "x_u8"):
-                    ws.x_u8 = torch.empty((B, self.S, self.S, 3), dtype=torch.uint8, device=dev)
-                dev_out = torch.empty((B, self.heads_out, self.S, self.S), dtype=out_dtype, device=dev)
-                host_out = torch.empty((B, self.heads_out, self.S, self.S), dtype=out_dtype).pin_memory()
-                slots[k] = (ws, dev_out, host_out)
-            ws, dev_out, host_out = slots[k]
-            if k in ev_free:
-                s_in.wait_event(ev_free[k])  # previous use of this slot fully drained (input consumed, output copied)
+            key = (B, out_dtype, depth, to_host)
+            bufs = self._stream_bufs.get(key)
+            if bufs is None:  # allocated once per (batch size, output kind): pinning memory is a slow, synchronising call
+                shp = (B, self.heads_out, self.S, self.S)
+                bufs = dict(dev=[torch.empty(shp, dtype=out_dtype, device=dev) for _ in range(depth)],
+                            host=[torch.empty(shp, dtype=out_dtype).pin_memory() for _ in range(n_host)] if to_host else [])
+                self._stream_bufs[key] = bufs
+            k = i % depth
+            ws = self._workspace(B, 100 + k)
+            if u8_in and not hasattr(ws, "x_u8"):
+                ws.x_u8 = torch.empty((B, self.S, self.S, 3), dtype=torch.uint8, device=dev)
+            dev_out = bufs["dev"][k]
+            if (B, k) in ev_free:
+                s_in.wait_event(ev_free[(B, k)])  # previous use of this slot fully drained
             else:
                 s_in.wait_stream(cur)
             with torch.cuda.stream(s_in):
@@ -376,15 +383,22 @@ class MipheiEngine:
             with torch.cuda.stream(s_run):
                 s_run.wait_event(e_in)
                 self._graph_for(ws, dev_out, ("stream", out_dtype, u8_in), u8_in).replay()
+                if device_sink is not None:
+                    device_sink(dev_out, i)
                 e_run = torch.cuda.Event()
                 e_run.record(s_run)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(e_run)
-                host_out.copy_(dev_out, non_blocking=True)
-                e_out = torch.cuda.Event()
-                e_out.record(s_out)
-            ev_free[k] = e_out
-            pending.append((e_out, host_out))
+            if to_host:
+                host_out = bufs["host"][i % n_host]
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(e_run)
+                    host_out.copy_(dev_out, non_blocking=True)
+                    e_out = torch.cuda.Event()
+                    e_out.record(s_out)
+                ev_free[(B, k)] = e_out
+                pending.append((e_out, host_out))
+            else:
+                ev_free[(B, k)] = e_run
+                pending.append((e_run, None))
             i += 1
             if len(pending) >= depth:
                 e, h = pending.pop(0)
@@ -394,6 +408,7 @@ class MipheiEngine:
             e.synchronize()
             yield h
         cur.wait_stream(s_out)
+        cur.wait_stream(s_run)
 
     # ------------------------------------------------------------------ public entry points
     def _out_dtype(self, x):

@@ -102,6 +102,14 @@ _SIGNATURES = {
                                   c_void_p]),
     "mv_cell_means_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
+    "mv_thumb_std_hist": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv_otsu_threshold": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "mv_tile_tissue": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "mv_stitch_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_i64, c_i64, c_int, c_void_p]),
+    "mv_host_alloc_mapped": (c_int, [c_i64, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "mv_host_free": (c_int, [c_void_p]),
+    "mv_host_register": (c_int, [c_void_p, c_i64]),
+    "mv_host_unregister": (c_int, [c_void_p]),
     "mv_loss_workspace_floats": (c_i64, [c_int, c_int, c_int]),
     "mv_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                 c_void_p, c_void_p, c_i64, c_void_p]),

@@ -608,3 +608,47 @@ def cell_means_bwd(dmeans, ids, counts, n_unique, nuclei, B, C, H, W):
     _lib.check(lib.mv_cell_means_bwd(_ptr(dmeans), _ptr(ids), _ptr(counts), _ptr(n_unique), _ptr(nuclei), nuclei.element_size(),
                                      B, C, H * W, _ptr(out), _stream()), "mv_cell_means_bwd")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- whole-slide plumbing
+def thumb_std_hist(thumb):
+    """uint8 [H, W, C] (C = 1..4) -> (np.uint8(thumb.std(-1)) as uint8 [H, W], histogram int32 [256]) (mv_thumb_std_hist)."""
+    lib = _lib_for(thumb)
+    assert thumb.dtype == torch.uint8 and thumb.dim() == 3 and thumb.is_contiguous() and 1 <= thumb.shape[2] <= 4
+    H, W, C = thumb.shape
+    std = torch.empty((H, W), dtype=torch.uint8, device=thumb.device)
+    hist = torch.empty(256, dtype=torch.int32, device=thumb.device)
+    _lib.check(lib.mv_thumb_std_hist(_ptr(thumb), H * W, C, _ptr(std), _ptr(hist), _stream()), "mv_thumb_std_hist")
+    return std, hist
+
+
+def otsu_threshold(hist, n_pix, out=None):
+    """the cv2 THRESH_OTSU threshold of an 8-bit image from its histogram -> device int32 [1] (mv_otsu_threshold)."""
+    lib = _lib_for(hist)
+    assert hist.dtype == torch.int32 and hist.numel() == 256 and hist.is_contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=torch.int32, device=hist.device)
+    _lib.check(lib.mv_otsu_threshold(_ptr(hist), int(n_pix), _ptr(out), _stream()), "mv_otsu_threshold")
+    return out
+
+
+def tile_tissue(mask_u8, boxes, thresh=None, fixed_thresh=0):
+    """counts int32 [n] of pixels > threshold inside each clipped box (x0, y0, x1, y1) of a uint8 [H, W] map (mv_tile_tissue)."""
+    lib = _lib_for(mask_u8)
+    assert mask_u8.dtype == torch.uint8 and mask_u8.dim() == 2 and mask_u8.is_contiguous()
+    assert boxes.dtype == torch.int32 and boxes.dim() == 2 and boxes.shape[1] == 4 and boxes.is_contiguous()
+    counts = torch.empty(boxes.shape[0], dtype=torch.int32, device=mask_u8.device)
+    _lib.check(lib.mv_tile_tissue(_ptr(mask_u8), mask_u8.shape[1], _ptr(thresh), int(fixed_thresh), _ptr(boxes), boxes.shape[0],
+                                  _ptr(counts), _stream()), "mv_tile_tissue")
+    return counts
+
+
+def stitch_tiles(tiles, xy, crop, keep, canvas_ptr, canvas_h, canvas_w, sequential=False):
+    """insert the [crop, crop + keep)^2 window of every uint8 tile [B, C, S, S] at canvas position xy[b] (mv_stitch_tiles);
+    canvas_ptr: device-addressable uint8 [C, canvas_h, canvas_w] (device tensor data_ptr or mapped pinned host memory)."""
+    lib = _lib_for(tiles)
+    assert tiles.dtype == torch.uint8 and tiles.dim() == 4 and tiles.is_contiguous() and tiles.shape[2] == tiles.shape[3]
+    assert xy.dtype == torch.int32 and xy.shape == (tiles.shape[0], 2) and xy.is_contiguous() and xy.device == tiles.device
+    B, C, S, _ = tiles.shape
+    _lib.check(lib.mv_stitch_tiles(_ptr(tiles), _ptr(xy), B, C, S, int(crop), int(keep), ctypes.c_void_p(int(canvas_ptr)),
+                                   int(canvas_h), int(canvas_w), 1 if sequential else 0, _stream()), "mv_stitch_tiles")

@@ -254,8 +254,10 @@ def test_stale_tape_raises_instead_of_returning_wrong_gradients():
 
 
 def test_trainer_graph_step_matches_autograd_step():
-    """Trainer.step (captured CUDA graphs, no autograd) and Trainer.step_autograd (model(x) / backward()) are the same
-    optimisation: identical loss trajectories and parameters over 4 steps (fp32 atomics allow last-bit differences)."""
+    """Trainer.step (captured CUDA graphs, no autograd), its eager twin and Trainer.step_autograd (model(x) / backward())
+    are the same optimisation: same gradients after the first step, same loss trajectory, same BatchNorm buffers and step
+    counters over 4 steps. (Weight-gradient sums are fp32 atomics: run-to-run last-bit noise, which Adam's early sign-like
+    updates amplify on near-zero gradients — parameters are compared by direction, not bit by bit.)"""
     from miphei_vit_b200.trainer import Trainer
 
     cfg = om.Config(img_size=128, embed_dim=128, depth=3, num_heads=2, hidden=256, out_chans=5)
@@ -268,15 +270,21 @@ def test_trainer_graph_step_matches_autograd_step():
         model = build(cfg, sd)
         tr = Trainer(model, marker_weights=w, base_lr=2e-3, total_steps=50, warmup_steps=2, use_graph=(mode == "graph"))
         step = tr.step_autograd if mode == "autograd" else tr.step
-        losses = [float(step(x, y).item()) for _ in range(4)]
-        runs.append((losses, tr.flat.detach().clone(), int(tr.step_dev.item()),
+        losses, g1 = [], None
+        for it in range(4):
+            losses.append(float(step(x, y).item()))
+            if it == 1:  # the graph path replays a captured graph from its second step on
+                g1 = tr.gflat.detach().clone()
+        runs.append((losses, tr.flat.detach().clone(), int(tr.step_dev.item()), g1,
                      {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}))
-    for losses, flat, nstep, bufs in runs[1:]:
+    ref = runs[0]
+    for losses, flat, nstep, g1, bufs in runs[1:]:
         assert nstep == 4
-        for a, b in zip(losses, runs[0][0]):
-            assert abs(a - b) < 2e-3 * abs(b), (losses, runs[0][0])
-        assert om.cosine(flat.cpu(), runs[0][1].cpu()) > 0.99999
+        for a, b in zip(losses, ref[0]):
+            assert abs(a - b) < 2e-3 * abs(b), (losses, ref[0])
+        assert om.cosine(g1.cpu(), ref[3].cpu()) > 0.9995
+        assert om.cosine(flat.cpu(), ref[1].cpu()) > 0.9995
         for k, v in bufs.items():
-            assert torch.allclose(v.float(), runs[0][3][k].float(), rtol=1e-3, atol=1e-5), k
-    assert runs[0][0][3] < runs[0][0][1]
-    assert int(runs[0][3]["decoder.fusion_blks.0.conv.bn.num_batches_tracked"]) == 4
+            assert torch.allclose(v.float(), ref[4][k].float(), rtol=2e-3, atol=1e-5), k
+    assert ref[0][3] < ref[0][1]
+    assert int(ref[4]["decoder.fusion_blks.0.conv.bn.num_batches_tracked"]) == 4

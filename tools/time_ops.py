@@ -60,7 +60,7 @@ if what == "infer":
 else:
     from miphei_vit_b200.trainer import Trainer
     y = torch.rand(B, 16, 256, 256, device="cuda") * 1.8 - 0.9
-    tr = Trainer(m, marker_weights=torch.linspace(1, 10, 16), batch_size=B)
+    tr = Trainer(m, marker_weights=torch.linspace(1, 10, 16), batch_size=B, use_graph=False)  # per-op events need eager launches
     run = lambda: tr.step(x, y)  # noqa: E731
 for _ in range(3):
     run()
