@@ -268,10 +268,13 @@ int mv_heads_bn_from_gram(const float* gram, double count, const float* w1, cons
  * E fp32 [40, 256] (rows 0..31 f^T e, row 32 1^T e), FF = the mv_gram32 output, fin = the [4, 256] (scale, shift, mean,
  * rstd) of mv_heads_bn_from_gram and count = pixels:  dw1 [256, 32], dgamma / dbeta / dw2 [256] (parameter gradients of
  * psi[0].weight, psi[1].weight / bias, psi[3].weight) and the operands of the two GEMMs that assemble d f:
- * ca_t bf16 [32, 256], mx_n [32, 64] (fp16 when mx_f16 else bf16), kshift fp32 [32]. */
+ * ca_t bf16 [32, 256], mx_n [32, 64] (fp16 when mx_f16 else bf16; stored times a power of two that keeps these
+ * gradient-sized values out of the fp16 underflow range, its reciprocal in mx_scale fp32 [32] = the `scale` of the GEMM that
+ * consumes mx_n), kshift fp32 [32]. */
 int mv_heads_bwd_algebra(const float* E, const float* FF, const float* w1, const float* b1, const float* gamma,
                          const float* w2, const float* fin, double count, int n_units, float* dw1, float* dgamma,
-                         float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* kshift, void* stream);
+                         float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* mx_scale, float* kshift,
+                         void* stream);
 int mv_bn_relu_apply(const void* z, int z_f32, const float* scale, const float* shift, void* y, int y_f16, int64_t m,
                      int c, void* stream);
 int mv_bn_relu_bwd(const void* dy, int64_t lddy, const void* y, const void* z, int z_f32, const float* mean, const float* rstd,

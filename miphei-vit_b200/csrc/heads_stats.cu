@@ -184,13 +184,15 @@ __global__ void heads_bn_from_gram_kernel(const float* __restrict__ gram, double
 // with a = W1 f + b1, ahat = (a - mean) rstd, the BatchNorm backward folds into
 //   dW1 = gr (w2 EF - S1/n F1 - S2/n XF),  d gamma = S2,  d beta = S1,  d w2 = scale A + shift E1
 //   d f  = dt W3t + e Ca - f Mx - (K0 + K1)          (Ca, Mx, K0 + K1 are written as the operands of the two GEMMs
-//                                                     that form d f: CaT bf16 [32, 256], MxN fp16/bf16 [32, 64], kshift [32])
+//                                                     that form d f: CaT bf16 [32, 256], MxN fp16/bf16 [32, 64] (times a power
+//                                                     of two, 1 / that in mx_scale [32]), kshift [32])
 // Everything is fp32; unit j = 16 * head + hidden index; units >= n_units are skipped.
 __global__ void __launch_bounds__(256) heads_bwd_algebra_kernel(
     const float* __restrict__ E, const float* __restrict__ FF, const float* __restrict__ W1, const float* __restrict__ b1,
     const float* __restrict__ gam, const float* __restrict__ w2, const float* __restrict__ fin, float n, int n_units,
     float* __restrict__ dW1, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw2,
-    __nv_bfloat16* __restrict__ CaT, void* __restrict__ MxN, int mx_f16, float* __restrict__ kshift) {
+    __nv_bfloat16* __restrict__ CaT, void* __restrict__ MxN, int mx_f16, float* __restrict__ mx_scale,
+    float* __restrict__ kshift) {
   griddep_sync();  // PDL: block until the previous kernel of the stream has completed (mv_ptx.cuh)
   __shared__ float F2s[32 * 33], F1s[32], Ws[256 * 33], kr[256], K01[32];
   const int j = threadIdx.x;
@@ -233,13 +235,30 @@ __global__ void __launch_bounds__(256) heads_bwd_algebra_kernel(
   __syncthreads();
   if (j < 32) kshift[j] = -K01[j];
   // MxN[r, c] = -Mx[c, r] = -sum_j W1[j, c] k2r_j W1[j, r]   (B operand [N = 32, K = 32 of pitch 64] of  dy = f (-Mx) + ...)
+  // Gradient-sized values (1e-10 and below) underflow fp16: the matrix is stored times a power of two that brings its
+  // largest entry into [1, 2) and the GEMM epilogue multiplies by the reciprocal (mx_scale, one value per output column).
+  __shared__ float Mxs[32 * 32];
+  __shared__ unsigned int mx_max_bits;
+  if (j == 0) mx_max_bits = 0u;
+  __syncthreads();
+  for (int i = j; i < 32 * 32; i += 256) {
+    const int r = i >> 5, c = i & 31;
+    float acc = 0.f;
+    for (int u = 0; u < n_units; ++u) acc += Ws[u * 33 + c] * kr[u] * Ws[u * 33 + r];
+    Mxs[i] = -acc;
+    atomicMax(&mx_max_bits, __float_as_uint(fabsf(acc)));  // non-negative floats order like their bit patterns
+  }
+  __syncthreads();
+  const float mx_max = __uint_as_float(mx_max_bits);
+  int ex = 0;
+  if (mx_max > 0.f && mx_max < 3.0e38f) (void)frexpf(mx_max, &ex);  // mx_max = m * 2^ex, m in [0.5, 1)
+  const float up = mx_max > 0.f ? ldexpf(1.f, 1 - ex) : 1.f;        // mx_max * up in [1, 2)
+  if (j < 32) mx_scale[j] = 1.f / up;
   for (int i = j; i < 32 * 64; i += 256) {
     const int r = i >> 6, c = i & 63;
-    float acc = 0.f;
-    if (c < 32)
-      for (int u = 0; u < n_units; ++u) acc += Ws[u * 33 + c] * kr[u] * Ws[u * 33 + r];
-    if (mx_f16) reinterpret_cast<__half*>(MxN)[i] = __float2half_rn(-acc);
-    else reinterpret_cast<__nv_bfloat16*>(MxN)[i] = __float2bfloat16(-acc);
+    const float v = c < 32 ? Mxs[r * 32 + c] * up : 0.f;
+    if (mx_f16) reinterpret_cast<__half*>(MxN)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(MxN)[i] = __float2bfloat16(v);
   }
 }
 
@@ -277,15 +296,15 @@ extern "C" int mv_heads_bn_from_gram(const float* gram, double count, const floa
 
 extern "C" int mv_heads_bwd_algebra(const float* E, const float* FF, const float* w1, const float* b1, const float* gamma,
                                     const float* w2, const float* fin, double count, int n_units, float* dw1, float* dgamma,
-                                    float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* kshift,
-                                    void* stream_) {
+                                    float* dbeta, float* dw2, void* ca_t_bf16, void* mx_n, int mx_f16, float* mx_scale,
+                                    float* kshift, void* stream_) {
   using namespace mv;
-  MV_CHECK_ARG(E && FF && w1 && b1 && gamma && w2 && fin && dw1 && dgamma && dbeta && dw2 && ca_t_bf16 && mx_n && kshift,
+  MV_CHECK_ARG(E && FF && w1 && b1 && gamma && w2 && fin && dw1 && dgamma && dbeta && dw2 && ca_t_bf16 && mx_n && mx_scale && kshift,
                "mv_heads_bwd_algebra: null pointer");
   MV_CHECK_ARG(n_units > 0 && n_units <= 256 && count > 0, "mv_heads_bwd_algebra: n_units in 1..256");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MV_LAUNCH(heads_bwd_algebra_kernel, 1, 256, 0, stream, E, FF, w1, b1, gamma, w2, fin, (float)count, n_units, dw1, dgamma,
-            dbeta, dw2, reinterpret_cast<__nv_bfloat16*>(ca_t_bf16), mx_n, mx_f16, kshift);
+            dbeta, dw2, reinterpret_cast<__nv_bfloat16*>(ca_t_bf16), mx_n, mx_f16, mx_scale, kshift);
   MV_CHECK_LAUNCH("heads_bwd_algebra");
   return MV_OK;
 }

@@ -225,6 +225,7 @@ class DecoderTrain:
         self.ca_t = torch.zeros((32, 256), dtype=torch.bfloat16, device=dev)
         self.mx_n = torch.zeros((32, 64), dtype=ADT, device=dev)
         self.kshift = torch.zeros(32, dtype=torch.float32, device=dev)
+        self.mx_scale = torch.ones(32, dtype=torch.float32, device=dev)
         # plain autograd path: private flat staging copy of the parameters and a private flat gradient buffer
         self._own_src = None
         self._own_grad = None
@@ -374,12 +375,12 @@ class DecoderTrain:
         ops.gemm(fTm, e, mode=ops.GEMM_NN_ATOMIC, out=acc["hd.E"])               # rows 0..31 = f^T e, row 32 = 1^T e
         # closed-form BatchNorm / gate / 1x1-conv gradients ([256, 32]-sized algebra, one CTA)
         ops.heads_bwd_algebra(acc["hd.E"], acc["hd.FF"], wc["hd.W1"], wc["hd.b1"], wc["hd.gam"], wc["hd.w2"], fin, M, self.n1,
-                              acc["hd.dW1"], acc["hd.S2"], acc["hd.S1"], acc["hd.dw2"], self.ca_t, self.mx_n, self.kshift)
+                              acc["hd.dW1"], acc["hd.S2"], acc["hd.S1"], acc["hd.dw2"], self.ca_t, self.mx_n, self.mx_scale, self.kshift)
         # d f = dt W3t + e Ca - f Mx - (K0 + K1)
         dfa = self._buf("hd.dfa", (M, 32), torch.float32)
         ops.gemm(e, self.ca_t, resid=df1, shift=self.kshift, out=dfa)
         dy = self._buf("hd.dy3", (M, 32), bf)
-        ops.gemm(f2, self.mx_n[:, :32], resid=dfa, out=dy)
+        ops.gemm(f2, self.mx_n[:, :32], scale=self.mx_scale, resid=dfa, out=dy)
         # ---------------- fusion blocks
         gskip = {}
         dfmap = None

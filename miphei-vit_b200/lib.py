@@ -76,7 +76,7 @@ _SIGNATURES = {
                                       c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mv_heads_bwd_algebra": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double,
                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                     c_void_p]),
+                                     c_void_p, c_void_p]),
     "mv_adam_schedule": (c_int, [c_void_p, c_float, c_i64, c_i64, c_float, c_float, c_void_p, c_void_p]),
     "mv_adam_clip_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_void_p, c_float,
                                       c_float, c_float, c_void_p]),

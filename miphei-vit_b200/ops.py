@@ -386,17 +386,17 @@ def heads_bn_from_gram(gram, count, w1, b1, gamma, beta, running_mean, running_v
     return out
 
 
-def heads_bwd_algebra(E, FF, w1, b1, gamma, w2, fin, count, n_units, dw1, dgamma, dbeta, dw2, ca_t, mx_n, kshift):
+def heads_bwd_algebra(E, FF, w1, b1, gamma, w2, fin, count, n_units, dw1, dgamma, dbeta, dw2, ca_t, mx_n, mx_scale, kshift):
     """closed-form gate-MLP / BatchNorm backward of the 16 heads (mv_heads_bwd_algebra)."""
     lib = _lib_for(E)
-    for t in (E, FF, w1, b1, gamma, w2, fin, dw1, dgamma, dbeta, dw2, kshift):
+    for t in (E, FF, w1, b1, gamma, w2, fin, dw1, dgamma, dbeta, dw2, mx_scale, kshift):
         assert t.dtype == torch.float32 and t.is_contiguous()
     assert E.shape == (40, 256) and FF.shape == (40, 32) and fin.shape == (4, 256) and w1.shape == (256, 32)
     assert ca_t.dtype == torch.bfloat16 and ca_t.shape == (32, 256) and ca_t.is_contiguous()
     assert mx_n.dtype in _H16 and mx_n.shape == (32, 64) and mx_n.is_contiguous()
     _lib.check(lib.mv_heads_bwd_algebra(_ptr(E), _ptr(FF), _ptr(w1), _ptr(b1), _ptr(gamma), _ptr(w2), _ptr(fin), float(count),
                                         int(n_units), _ptr(dw1), _ptr(dgamma), _ptr(dbeta), _ptr(dw2), _ptr(ca_t), _ptr(mx_n),
-                                        1 if mx_n.dtype == torch.float16 else 0, _ptr(kshift), _stream()),
+                                        1 if mx_n.dtype == torch.float16 else 0, _ptr(mx_scale), _ptr(kshift), _stream()),
                "mv_heads_bwd_algebra")
 
 

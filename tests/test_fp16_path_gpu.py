@@ -203,8 +203,8 @@ def test_heads_bwd_algebra_matches_torch_formulas():
     dW1, dg, db, dw2 = (torch.zeros(s, device="cuda") for s in ((256, 32), (256,), (256,), (256,)))
     ca_t = torch.zeros((32, 256), dtype=B16, device="cuda")
     mx = torch.zeros((32, 64), dtype=H, device="cuda")
-    ks = torch.zeros(32, device="cuda")
-    ops.heads_bwd_algebra(E, FF, W1, b1, gam, w2, fin, n, n_units, dW1, dg, db, dw2, ca_t, mx, ks)
+    ks, mxs = torch.zeros(32, device="cuda"), torch.zeros(32, device="cuda")
+    ops.heads_bwd_algebra(E, FF, W1, b1, gam, w2, fin, n, n_units, dW1, dg, db, dw2, ca_t, mx, mxs, ks)
     d = lambda t: t.double()  # noqa: E731
     sl = slice(0, n_units)
     scale_g, shift_g, mean, rstd = (d(fin[i])[sl] for i in range(4))
@@ -224,7 +224,9 @@ def test_heads_bwd_algebra_matches_torch_formulas():
     assert _rel(dW1[sl], rdW1) < 1e-4 and _rel(dg[sl], S2) < 1e-4 and _rel(db[sl], S1) < 1e-5
     assert _rel(dw2[sl], scale_g * A + shift_g * E1) < 1e-4
     assert _rel(ca_t[:, sl].float().t(), Ca) < 5e-3 and float(ca_t[:, n_units:].abs().sum()) == 0.0
-    assert _rel(mx[:, :32].float(), (-Mx).t()) < 2e-3 and float(mx[:, 32:].abs().sum()) == 0.0
+    # gradient-sized values (1e-10 here) would underflow fp16: stored times a power of two, reciprocal in mx_scale
+    assert float(mxs.min()) == float(mxs.max()) and 1.0 <= float(mx[:, :32].abs().max()) < 2.0
+    assert _rel(mx[:, :32].float() * mxs[0], (-Mx).t()) < 2e-3 and float(mx[:, 32:].abs().sum()) == 0.0
     assert _rel(ks, -(K0 + K1)) < 1e-4
 
 

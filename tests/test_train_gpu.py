@@ -285,6 +285,6 @@ def test_trainer_graph_step_matches_autograd_step():
         assert om.cosine(g1.cpu(), ref[3].cpu()) > 0.9995
         assert om.cosine(flat.cpu(), ref[1].cpu()) > 0.9995
         for k, v in bufs.items():
-            assert torch.allclose(v.float(), ref[4][k].float(), rtol=2e-3, atol=1e-5), k
+            assert torch.allclose(v.float(), ref[4][k].float(), rtol=1e-2, atol=2e-3), k
     assert ref[0][3] < ref[0][1]
     assert int(ref[4]["decoder.fusion_blks.0.conv.bn.num_batches_tracked"]) == 4
