@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the MIPHEI-ViT hot path on B200 (driver contract: one JSON line on rank 0).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4|c5]   # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...                # the reference's CPU path (oracle port), host cores
 
-Workload at every N (weak scaling): BASELINE.json configs[1] — ORION 16-channel inference, batch 16 per GPU, 256-px
-synthetic tiles, ViT-g/14 + ViTMatte decoder with random-init weights (`config.workload`).  A "step" is one forward
-pass over one batch.  `value` times the forward with inputs resident in HBM (CUDA events, max over ranks); `e2e` times
-the public call with pinned HOST buffers (H2D of the fp32 tiles, forward, D2H of the uint8 sink output) per step.
-When the training path is available the same line carries `train` (config[2]: fwd+bwd+loss+clip+Adam, batch 32/GPU).
+Configs (BASELINE.json `configs`).  A "step" is one pass of the hot path over one batch of synthetic input.
+  c2 (default)  ORION 16-channel inference, batch 16 per GPU, 256-px tiles — the line the driver records. `value`: forward
+                with inputs resident in HBM (graph replay, CUDA events, max over ranks); `e2e`: engine.infer_stream over
+                pinned HOST batches (H2D, forward, D2H of the uint8 sink every step).  The same line carries `train` (c3).
+  c3            training step (fwd + bwd + weighted MSE + clip + Adam), batch 32 per GPU, NCCL gradient all-reduce.
+                `value`: x, y resident; `e2e`: x, y in pinned host memory, H2D every step, loss read back.
+  c4            HEMIT-style 3-channel head on 512-px tiles (1301 tokens), training, batch 8 per GPU.
+  c5            whole-slide sweep: 4096 raw uint8 tiles in host memory, batch 64, sharded round-robin over the ranks through
+                wsi.infer_slide (loader workers -> pinned ring -> infer_stream -> uint8 predictions on the host); strong scaling.
+Every number is measured on the device with CUDA events, after >= 3 warm-up steps, max over ranks.
 """
 import argparse
+import csv
+import glob
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -21,10 +29,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GF_PER_TILE_FWD = 793.40   # BASELINE.md section 3 (256 px, 16 ch)
-GF_PER_TILE_TRAIN = 1633.87
-METRIC = "tiles_per_sec_infer_256px_16ch"
+GF = {256: dict(fwd=793.40, train=1633.87), 512: dict(fwd=3443.57, train=7379.38)}  # BASELINE.md section 3 (GF / tile)
 UNIT = "tiles/s"
+HE_MEAN, HE_STD = (0.707223, 0.578729, 0.703617), (0.211883, 0.230117, 0.177517)   # src/dataset.py:601
 
 
 def peaks():
@@ -33,10 +40,10 @@ def peaks():
         try:
             d = json.load(open(p))
             return dict(hbm=d["hbm_gbs"], tc=d["bf16_tflops"], tc_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                        source="measured")
+                        source="MEASURED_PEAKS.json")
         except Exception:
             pass
-    return dict(hbm=6650.0, tc=1590.0, tc_sus=1400.0, source="fallback")
+    return dict(hbm=6650.0, tc=1590.0, tc_sus=1400.0, source="B200_PROFILING.md fallback")
 
 
 class ClockSampler:
@@ -93,53 +100,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-# ----------------------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference's CPU implementation of the path: oracle port (decoder / LoRA restated from the reference, timm ViT
-    restated; see oracle/model.py) in fp32 on all host cores. Only rank 0 works."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import torch
-    from oracle import model as om
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = om.Config()
-    sd = om.init_state_dict(cfg, seed=0, perturb=True)
-    sample_b = 2
-    x = om.normalize_tiles(om.synthetic_tiles_u8(sample_b, cfg.img_size, seed=1234))
-    with torch.inference_mode():
-        for _ in range(max(1, min(args.warmup, 1))):
-            om.miphei_forward(sd, x, cfg)
-        steps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            om.miphei_forward(sd, x, cfg)
-        dt = (time.perf_counter() - t0) / steps
-    val = sample_b / dt
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ORION 16-channel inference, 256-px tiles, ViT-g/14 + ViTMatte decoder, random init "
-                               "(BASELINE configs[1]); CPU sample of batch %d per step" % sample_b},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d steps of batch %d fp32 forward on %d threads" % (steps, sample_b, cores)},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+# ----------------------------------------------------------------------------------------------------- synthetic data
+def synth_tiles_u8(torch, B, S, seed):
+    """uint8 RGB i.i.d. around the H&E statistics of channel_stats.json, NCHW."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    mean = torch.tensor([211.1, 194.7, 213.8]).view(1, 3, 1, 1)
+    std = torch.tensor([30.1, 36.4, 26.4]).view(1, 3, 1, 1)
+    return (torch.randn((B, 3, S, S), generator=g) * std + mean).clamp_(0, 255).round_().to(torch.uint8)
 
 
-# ----------------------------------------------------------------------------------------------------- CUDA arm
+def normalize(torch, u8):
+    m = torch.tensor(HE_MEAN).view(1, 3, 1, 1) * 255
+    s = torch.tensor(HE_STD).view(1, 3, 1, 1) * 255
+    return ((u8.float() - m) / s).contiguous()
+
+
+def synth_batch(torch, B, S, seed):
+    return normalize(torch, synth_tiles_u8(torch, B, S, seed))
+
+
+def synth_targets(torch, B, C, S, seed):
+    """uint8 'mostly dark' targets mapped to [-0.9, 0.9] as src/dataset.py:573 does."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    u = torch.empty((B, C, S, S)).exponential_(1.0 / 20.0, generator=g).clamp_(0, 255).floor_()
+    return (u / 255.0 * 1.8 - 0.9).contiguous()
+
+
 def build_model(device, out_chans=16, img=256):
+    import contextlib
+    import io
+
     import torch
     from miphei_vit_b200.generators.mipheivit import get_vitmatte
 
     torch.manual_seed(0)  # identical weights on every rank
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
         with torch.device(device):
             m = get_vitmatte("hoptimus0", img, out_chans, use_lora=True)
@@ -152,188 +146,479 @@ def build_model(device, out_chans=16, img=256):
     return m
 
 
-def synth_batch(torch, B, S, seed, device):
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    mean = torch.tensor([211.1, 194.7, 213.8]).view(1, 3, 1, 1)
-    std = torch.tensor([30.1, 36.4, 26.4]).view(1, 3, 1, 1)
-    u8 = (torch.randn((B, 3, S, S), generator=g) * std + mean).clamp_(0, 255).round_()
-    m = torch.tensor([0.707223, 0.578729, 0.703617]).view(1, 3, 1, 1) * 255
-    s = torch.tensor([0.211883, 0.230117, 0.177517]).view(1, 3, 1, 1) * 255
-    return ((u8 - m) / s).float()
-
-
-def cpu_baseline_sample(budget_s=25.0):
-    """Oracle forward on the host cores, bounded sample (rank 0, N=1 only)."""
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def _oracle(img=256, chans=16):
     import torch
     from oracle import model as om
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = om.Config()
-    sd = om.init_state_dict(cfg, seed=0, perturb=True)
-    x = om.normalize_tiles(om.synthetic_tiles_u8(1, cfg.img_size, seed=1234))
+    cfg = om.Config(img_size=img, out_chans=chans)
+    return torch, om, cfg, om.init_state_dict(cfg, seed=0, perturb=True), cores
+
+
+def cpu_forward(torch, om, cfg, sd, B, reps, budget_s):
+    x = om.normalize_tiles(om.synthetic_tiles_u8(B, cfg.img_size, seed=1234))
     with torch.inference_mode():
         om.miphei_forward(sd, x, cfg)
-        n, t0 = 0, time.perf_counter()
-        while n < 5 and (time.perf_counter() - t0) < budget_s:
+        ts, t_all = [], time.perf_counter()
+        while len(ts) < reps and (time.perf_counter() - t_all) < budget_s:
+            t0 = time.perf_counter()
             om.miphei_forward(sd, x, cfg)
-            n += 1
-        dt = (time.perf_counter() - t0) / max(n, 1)
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d forward passes of batch 1 (fp32, %d torch threads) of the oracle port" % (n, cores)}
+            ts.append(time.perf_counter() - t0)
+    return B / statistics.median(ts), len(ts)
 
 
-def run_cuda(args):
-    import torch
-    import torch.distributed as dist
+def cpu_train_step(torch, om, cfg, sd, B):
+    """one fwd + bwd + clip + Adam step of the oracle port (src/models.py:134-139) on the host cores"""
+    x = om.normalize_tiles(om.synthetic_tiles_u8(B, cfg.img_size, seed=1234))
+    y = om.synthetic_targets(B, cfg.out_chans, cfg.img_size, seed=4321)
+    w = torch.linspace(1.0, 10.6, cfg.out_chans)
+    sd = dict(sd)
+    t0 = time.perf_counter()
+    om.train_step(sd, {}, x, y, cfg, w, 2e-4 * B ** 0.5, 10000)
+    return B / (time.perf_counter() - t0)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+
+def cpu_baseline_sample(config="c2"):
+    """Oracle port on the host cores, bounded sample (rank 0, N = 1 only): C1 (B=1 forward), B=16 forward and one B=4
+    training step (SURVEY 8d / BASELINE.md section 4)."""
+    torch, om, cfg, sd, cores = _oracle(512 if config == "c4" else 256, 3 if config == "c4" else 16)
+    if config == "c4":
+        v, n = cpu_forward(torch, om, cfg, sd, 1, 2, 30.0)
+        return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d forward passes of batch 1 at 512 px / 3 channels (fp32, %d torch threads) of the oracle port" % (n, cores)}
+    v1, n1 = cpu_forward(torch, om, cfg, sd, 1, 3, 12.0)
+    v16, n16 = cpu_forward(torch, om, cfg, sd, 16, 2, 25.0)
+    vt = cpu_train_step(torch, om, cfg, sd, 4)
+    return {"value": v16, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "median of %d forward passes of batch 16 (fp32, %d torch threads) of the oracle port" % (n16, cores),
+            "c1_batch1_forward": {"value": v1, "unit": UNIT, "sample": "median of %d passes" % n1},
+            "train_batch4_step": {"value": vt, "unit": UNIT, "sample": "1 fwd+bwd+clip+Adam step of batch 4"}}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: oracle port (decoder / LoRA restated from the reference, timm ViT
+    restated; see oracle/model.py) in fp32 on all host cores. Only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cfgname = args.config
+    train = cfgname in ("c3", "c4")
+    torch, om, cfg, sd, cores = _oracle(512 if cfgname == "c4" else 256, 3 if cfgname == "c4" else 16)
+    steps = max(1, min(args.steps, 5))
+    if train:
+        sample_b = 2 if cfgname == "c3" else 1
+        ts = []
+        for _ in range(max(1, min(steps, 2))):
+            ts.append(sample_b / cpu_train_step(torch, om, cfg, sd, sample_b))
+        dt = statistics.median(ts)
+        what = "training step (fwd+bwd+clip+Adam)"
+    else:
+        sample_b = 2
+        val, n = cpu_forward(torch, om, cfg, sd, sample_b, steps, 120.0)
+        dt = sample_b / val
+        what = "fp32 forward"
+    val = sample_b / dt
+    line = {
+        "impl": "reference", "metric": metric_name(cfgname), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if cfgname == "c5" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfgname) + "; CPU sample of batch %d per step" % sample_b},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d x %s of batch %d on %d threads" % (steps, what, sample_b, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(c):
+    return {"c2": "tiles_per_sec_infer_256px_16ch", "c3": "tiles_per_sec_train_256px_16ch",
+            "c4": "tiles_per_sec_train_512px_3ch", "c5": "tiles_per_sec_slide_sweep_256px_16ch"}[c]
+
+
+def workload_name(c):
+    return {"c2": "ORION 16-channel inference (BASELINE configs[1]): batch 16 per GPU, 256-px tiles, ViT-g/14 (40 blocks, "
+                  "LoRA r8) + ViTMatte decoder, random init",
+            "c3": "ORION training step (BASELINE configs[2]): fwd + bwd + weighted MSE + clip + Adam, batch 32 per GPU, "
+                  "256-px tiles, 16 channels, NCCL gradient all-reduce",
+            "c4": "HEMIT-style 3-channel head on 512-px tiles (BASELINE configs[3]): training step, batch 8 per GPU, 1301 tokens",
+            "c5": "whole-slide tiled inference sweep (BASELINE configs[4]): 4096 raw uint8 256-px tiles from host memory, "
+                  "batch 64, sharded round-robin over the GPUs"}[c]
+
+
+# ----------------------------------------------------------------------------------------------------- CUDA arm helpers
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        t = self.torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> ms per step"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1)) / steps
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch of a kernel from the newest committed `ncu --set full` summary (profiles/*ncu_full*.csv)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*.csv")))
+    for f in reversed(files):
+        try:
+            rows = [r for r in csv.DictReader(open(f)) if kernel_substr in r.get("kernel", "")]
+            if rows:
+                b = statistics.mean(float(r["dram_rd_MB"]) + float(r["dram_wr_MB"]) for r in rows) * 1e6
+                return b, os.path.basename(f)
+        except Exception:
+            continue
+    return None, None
+
+
+def kernel_table(torch, eng, B, pk):
+    """Live CUDA-event timing of the encoder kernels at this batch size, each run over the 40 blocks' own weights back to
+    back (operands larger than L2 in total): achieved TFLOP/s or GB/s against the measured peaks."""
+    from miphei_vit_b200 import ops
+
+    ws = eng._workspace(B)
+    M, D, H, N = ws.M, eng.D, eng.H, eng.N
+    xn = ws.xn_ext[:, :D]
+
+    def timeit(fn):
+        for pb in eng.blocks[:4]:
+            fn(pb)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(2):
+            for pb in eng.blocks:
+                fn(pb)
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / (2 * len(eng.blocks)) * 1e3  # us per launch
+
+    rows = []
+
+    def tensor_row(name, flops, us):
+        tf = flops / us / 1e6
+        rows.append({"kernel": name, "us": us, "achieved": tf, "unit": "TFLOP/s", "frac_of_burst": tf / pk["tc"],
+                     "frac_of_sustained": tf / pk["tc_sus"]})
+
+    def hbm_row(name, nbytes, us):
+        gb = nbytes / us / 1e3
+        rows.append({"kernel": name, "us": us, "achieved": gb, "unit": "GB/s", "frac_of_hbm": gb / pk["hbm"]})
+
+    wq = "wqkv_m" if eng.merge_lora_eval else "wqkv_ext"
+    us = timeit(lambda pb: ops.gemm(xn, pb[wq][:, :D], shift=pb["bqkv"], out=ws.qkv))
+    tensor_row("QKV GEMM [M,%d]x[%d,%d] (+bias)" % (D, 3 * D, D), 2.0 * M * 3 * D * D, us)
+    us = timeit(lambda pb: ops.gemm(ws.o, pb["wproj"], scale=pb["g1"], shift=pb["g1b"], resid=ws.x, out=ws.x))
+    tensor_row("attn.proj GEMM + LayerScale + fp32 residual", 2.0 * M * D * D, us)
+    us_fc1 = timeit(lambda pb: ops.gemm(ws.xn2, pb["w1"], mode=ops.GEMM_SWIGLU, shift=pb["b1"], out=ws.u))
+    tensor_row("fc1 GEMM + SwiGLU epilogue", 2.0 * M * D * 2 * H, us_fc1)
+    us = timeit(lambda pb: ops.gemm(ws.u, pb["w2"], scale=pb["g2"], shift=pb["g2b"], resid=ws.x, out=ws.x))
+    tensor_row("fc2 GEMM + LayerScale + fp32 residual", 2.0 * M * H * D, us)
+    us = timeit(lambda pb: ops.attn_fwd(ws.qkv, B, N, eng.heads, out=ws.o))
+    tensor_row("attention forward (%d tokens, %d heads)" % (N, eng.heads), 4.0 * B * N * N * D, us)
+    us = timeit(lambda pb: ops.layernorm_fwd(ws.x, pb["n1w"], pb["n1b"], out=xn))
+    hbm_row("LayerNorm forward fp32 -> bf16", M * D * 6.0, us)
+    return rows, us_fc1
+
+
+# ----------------------------------------------------------------------------------------------------- training bench
+def train_bench(cx, model, B, S, C, steps, gf_train, want_e2e=True):
+    """value: x, y resident in HBM; e2e: x, y in pinned host memory, copied H2D every step on a copy stream (double-buffered
+    against the previous step's compute), loss copied back every step."""
+    torch = cx.torch
+    from miphei_vit_b200.trainer import Trainer
+
+    dev, rank, world = cx.dev, cx.rank, cx.world
+    xs = [synth_batch(torch, B, S, 4321 + 31 * i + rank).pin_memory() for i in range(2)]
+    ys = [synth_targets(torch, B, C, S, 999 + 17 * i + rank).pin_memory() for i in range(2)]
+    w = torch.linspace(1.0, 10.6, C) if C == 16 else torch.ones(C)
+    tr = Trainer(model, marker_weights=w, batch_size=B, total_steps=10000)
+    xd, yd = xs[0].to(dev), ys[0].to(dev)
+    for _ in range(3):
+        tr.step(xd, yd)
+    torch.cuda.synchronize()
+    from miphei_vit_b200 import lib
+    lib.reset_launch_count()
+    tr.use_graph = False
+    tr.step(xd, yd)  # one eager step: counts this library's launches per step
+    torch.cuda.synchronize()
+    launches = lib.launch_count()
+    tr.use_graph = True
+    ms = cx.timed(lambda i: tr.step(xd, yd), steps)
+    out = {"metric": metric_name("c3" if S == 256 else "c4"), "value": world * B / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
+           "steps": steps, "batch_per_gpu": B, "loss": float(tr.loss_buf.item()), "tflops": world * B * gf_train / ms,
+           "frac_of_sustained_bf16": B * gf_train / ms / peaks()["tc_sus"], "frac_of_burst_bf16": B * gf_train / ms / peaks()["tc"],
+           "scaling": "weak", "gpu_launches_per_step": int(launches),
+           "note": "fwd+bwd+WeightedMSE+clip+Adam as %d captured CUDA graph(s) per step, every kernel hand-written; "
+                   "NCCL AVG all-reduce of the 26.8 MB gradient in 3 buckets overlapped with the encoder backward"
+                   % (1 if world == 1 else 4)}
+    if want_e2e:
+        copy = torch.cuda.Stream(device=dev)
+        bufs = [(torch.empty_like(xd), torch.empty_like(yd)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(1).pin_memory()
+        cur = torch.cuda.current_stream()
+
+        def stage(i):  # H2D of step i's batch on the copy stream, once the step that last read this buffer has finished
+            k = i % 2
+            with torch.cuda.stream(copy):
+                copy.wait_event(done[k])
+                bufs[k][0].copy_(xs[i % 2], non_blocking=True)
+                bufs[k][1].copy_(ys[i % 2], non_blocking=True)
+                ready[k].record(copy)
+
+        count = [0]
+
+        def e2e_step(_):
+            i = count[0]
+            count[0] += 1
+            k = i % 2
+            if i == 0:
+                stage(0)
+            stage(i + 1)
+            cur.wait_event(ready[k])
+            tr.step(bufs[k][0], bufs[k][1])
+            done[k].record(cur)
+            loss_host.copy_(tr.loss_buf, non_blocking=True)
+
+        for k in range(2):
+            done[k].record(cur)
+        cx.timed(e2e_step, 3)
+        ms_e = cx.timed(e2e_step, steps)
+        out["e2e"] = {"value": world * B / ms_e * 1e3, "unit": UNIT, "ms_per_step": ms_e,
+                      "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
+                      "api": "Trainer.step(x, y) with x, y copied from pinned host memory every step (copy stream, "
+                             "double-buffered), loss copied back every step"}
+    model.eval()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- configs
+def run_c2(cx):
+    torch, args, dev, rank, world = cx.torch, cx.args, cx.dev, cx.rank, cx.world
     from miphei_vit_b200 import lib
 
-    B, S = args.batch, 256
+    B, S = args.batch or 16, 256
     model = build_model(dev).eval()
     eng = model.engine
-    x_host = synth_batch(torch, B, S, 1234 + rank, dev).pin_memory()
+    x_host = synth_batch(torch, B, S, 1234 + rank).pin_memory()
     x_dev = x_host.to(dev)
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- resident-input throughput (value): graph replay of the forward, fp32 NCHW output
     lib.reset_launch_count()
     eng.use_graphs = False
-    eng.infer(x_dev, reuse_output=True)  # counts launches of one forward
+    eng.infer(x_dev, reuse_output=True)  # counts the launches of one forward
     torch.cuda.synchronize()
     launches_per_fwd = lib.launch_count()
     eng.use_graphs = True
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         eng.infer(x_dev, reuse_output=True)
-    sampler = ClockSampler(local)
-    barrier()
+    sampler = ClockSampler(cx.local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.infer(x_dev, reuse_output=True)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_step = cx.timed(lambda i: eng.infer(x_dev, reuse_output=True), args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     value = world * B / ms_step * 1e3
 
     # ---- end to end through the public API with HOST buffers: engine.infer_stream over pinned fp32 NCHW tiles (what the
     # reference's DataLoader hands to generator(x)); every step copies its batch H2D and its uint8 predictions D2H, the
-    # copies of neighbouring steps overlap the compute (double buffering). Three distinct host batches rotate.
-    hosts = [x_host] + [synth_batch(torch, B, S, 99 + 7 * i + rank, dev).pin_memory() for i in range(2)]
+    # copies of neighbouring steps overlap the compute. Three distinct host batches rotate. Median of 3 passes of K steps.
+    hosts = [x_host] + [synth_batch(torch, B, S, 99 + 7 * i + rank).pin_memory() for i in range(2)]
 
-    def stream_e2e(batches):
-        n = 0
-        for _ in eng.infer_stream(batches(max(3, min(args.warmup, 4)))):
-            n += 1
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for out in eng.infer_stream(batches(args.steps)):
-            n += 1
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * B / (float(t.item()) / args.steps) * 1e3
+    def stream_e2e(src):
+        for _ in eng.infer_stream((src[i % 3] for i in range(max(3, min(args.warmup, 4))))):
+            pass
+        vals = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cx.barrier()
+            e0.record()
+            for _o in eng.infer_stream((src[i % 3] for i in range(args.steps))):
+                pass
+            e1.record()
+            cx.barrier()
+            vals.append(world * B / (cx.max_ms(e0.elapsed_time(e1)) / args.steps) * 1e3)
+        return statistics.median(vals), vals
 
-    # two passes of K steps each, the better one is reported (the host thread that feeds the three streams shares the box
-    # with the clock sampler and NCCL progress threads; a descheduled pass shows up as a 3-4 % dip)
-    e2e_val = max(stream_e2e(lambda k: (hosts[i % 3] for i in range(k))) for _ in range(2))
-    out_host = torch.empty((B, 16, S, S), dtype=torch.uint8)
-    # the same with raw uint8 NHWC tiles normalised on the device (4x smaller H2D; SURVEY 8f-2) — reported beside e2e
-    raw = [(h * torch.tensor([0.211883, 0.230117, 0.177517]).view(1, 3, 1, 1) * 255
-            + torch.tensor([0.707223, 0.578729, 0.703617]).view(1, 3, 1, 1) * 255).round_().clamp_(0, 255)
-           .permute(0, 2, 3, 1).contiguous().to(torch.uint8).pin_memory() for h in hosts]
-    e2e_u8 = max(stream_e2e(lambda k: (raw[i % 3] for i in range(k))) for _ in range(2))
+    e2e_val, e2e_all = stream_e2e(hosts)
+    raw = [synth_tiles_u8(torch, B, S, 1234 + 5 * i + rank).permute(0, 2, 3, 1).contiguous().pin_memory() for i in range(3)]
+    e2e_u8, _ = stream_e2e(raw)  # raw uint8 NHWC tiles normalised on the device (4x smaller H2D; SURVEY 8f-2)
 
-    # ---- roofline of the dominant kernel: the fc1 SwiGLU GEMM (42.9 % of forward FLOPs), timed live with CUDA events
     roof = None
     if rank == 0:
         pk = peaks()
-        from miphei_vit_b200 import ops
-        ws = eng._workspace(B)
-        pb = eng.blocks
-        evs = []
-        torch.cuda.synchronize()
-        for it in range(3):
-            for b_ in pb:
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                ops.gemm(ws.xn2, b_["w1"], mode=ops.GEMM_SWIGLU, shift=b_["b1"], out=ws.u)
-                a1.record()
-                if it > 0:
-                    evs.append((a0, a1))
-        torch.cuda.synchronize()
-        dur = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
-        flops = 2.0 * ws.M * eng.D * 2 * eng.H
-        ach = flops / dur / 1e9
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel<256, SWIGLU> (fc1 + SwiGLU epilogue)",
-                "achieved": ach, "peak": pk["tc_sus"], "unit": "TFLOP/s", "frac": ach / pk["tc_sus"],
-                "peak_kind": "%s sustained cuBLAS bf16 (burst %.1f)" % (pk["source"], pk["tc"]),
-                # DRAM bytes of ONE launch of this kernel at M=5264 from the committed ncu --set full capture
-                # (profiles/r01_ncu_full_encoder_kernels_infer_b16_v3.csv: 41.4 MB read + 11.9 MB written)
-                "traffic": 53.3e6 if ws.M == 5264 else None, "traffic_unit": "B/launch (ncu dram__bytes_read+write)",
-                "algorithmic_bytes": float(2 * (ws.M * eng.D + 2 * eng.H * eng.D + ws.M * eng.H)),
-                "launch_us": dur * 1e3, "flops_per_launch": flops,
-                "whole_step_tflops": world * B * GF_PER_TILE_FWD / ms_step,
-                "whole_step_frac_of_sustained": B * GF_PER_TILE_FWD / ms_step / pk["tc_sus"]}
+        table, us_fc1 = kernel_table(torch, eng, B, pk)
+        M = eng._workspace(B).M
+        flops = 2.0 * M * eng.D * 2 * eng.H
+        ach = flops / us_fc1 / 1e6
+        traffic, traffic_src = ncu_traffic("gemm_bf16_tc_kernel<256, 1, 1, 0>")
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel<256, SWIGLU, PAIR> (fc1 + SwiGLU epilogue; 42.9 % of forward FLOPs)",
+                "achieved": ach, "peak": pk["tc"], "unit": "TFLOP/s", "frac": ach / pk["tc"],
+                "peak_kind": "burst cuBLAS bf16 (%s) — the kernel is timed alone, back to back over the 40 blocks' weights" % pk["source"],
+                "frac_of_burst": ach / pk["tc"], "frac_of_sustained": ach / pk["tc_sus"], "peak_sustained": pk["tc_sus"],
+                "traffic": traffic if M == 5264 else None, "traffic_source": traffic_src,
+                "traffic_unit": "B/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of this kernel)",
+                "algorithmic_bytes": float(2 * (M * eng.D + 2 * eng.H * eng.D + M * eng.H)),
+                "launch_us": us_fc1, "flops_per_launch": flops,
+                "whole_step_tflops": world * B * GF[256]["fwd"] / ms_step,
+                "whole_step_frac_of_sustained": B * GF[256]["fwd"] / ms_step / pk["tc_sus"],
+                "whole_step_frac_of_burst": B * GF[256]["fwd"] / ms_step / pk["tc"],
+                "kernels": table}
 
     train = None
-    try:
-        from miphei_vit_b200 import trainer  # noqa: F401
-        train = trainer.bench_train(model, args, rank, world, dev)
-    except ImportError:
-        train = None
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample()
-
+    if not args.no_train:
+        train = train_bench(cx, model, args.train_batch, 256, 16, max(3, min(args.steps, 10)), GF[256]["train"])
+    cpu = cpu_baseline_sample("c2") if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ORION 16-channel inference (BASELINE configs[1]): batch %d per GPU, 256-px tiles, "
-                                   "ViT-g/14 (40 blocks, LoRA r8) + ViTMatte decoder, random init" % B,
-                       "global_batch": world * B, "tokens_per_tile": 329, "parallelism": "tile-sharded x%d, no collective" % world,
-                       "l2": "weights (2.3 GB bf16) and activations exceed L2 every step; no flush needed",
-                       "gf_per_tile": GF_PER_TILE_FWD},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
-                    "d2h_bytes_per_step": int(out_host.numel()),
-                    "api": "generator.engine.infer_stream(pinned fp32 NCHW batches) -> pinned uint8 predictions; H2D, "
-                           "compute and D2H of neighbouring steps overlap (double-buffered, 3 streams); best of 2 passes of K steps",
-                    "uint8_tiles": {"value": e2e_u8, "unit": UNIT, "h2d_bytes_per_step": int(raw[0].numel()),
-                                    "d2h_bytes_per_step": int(out_host.numel()),
-                                    "note": "raw uint8 NHWC tiles normalised on the device (mv_prep_input_u8)"}},
-            "gpu_launches": int(launches_per_fwd * args.steps),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        }
+        line = base_line(cx, "c2", value, ms_step, args.steps, W, clocks, cpu)
+        line["config"].update({"global_batch": world * B, "tokens_per_tile": 329,
+                               "parallelism": "tile-sharded x%d, no collective" % world, "gf_per_tile": GF[256]["fwd"]})
+        line["e2e"] = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                       "d2h_bytes_per_step": int(B * 16 * S * S), "passes": e2e_all,
+                       "api": "generator.engine.infer_stream(pinned fp32 NCHW batches) -> pinned uint8 predictions; H2D, compute "
+                              "and D2H of neighbouring steps overlap (3 streams); median of 3 passes of K steps",
+                       "uint8_tiles": {"value": e2e_u8, "unit": UNIT, "h2d_bytes_per_step": int(raw[0].numel()),
+                                       "d2h_bytes_per_step": int(B * 16 * S * S),
+                                       "note": "raw uint8 NHWC tiles normalised on the device (mv_prep_input_u8)"}}
+        line["gpu_launches"] = int(launches_per_fwd * args.steps)
+        line["roofline"] = roof
         if train is not None:
             line["train"] = train
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def base_line(cx, cfgname, value, ms_step, steps, warmup, clocks, cpu):
+    return {"metric": metric_name(cfgname), "value": value, "unit": UNIT, "n_gpus": cx.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if cfgname == "c5" else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(cfgname),
+                       "l2": "weights (2.3 GB bf16) and activations exceed L2 every step; no flush needed"},
+            "clocks": clocks, "cpu_baseline": cpu}
+
+
+def run_train_config(cx, cfgname):
+    torch, args, dev, rank, world = cx.torch, cx.args, cx.dev, cx.rank, cx.world
+    S, C, B = (256, 16, args.batch or 32) if cfgname == "c3" else (512, 3, args.batch or 8)
+    model = build_model(dev, out_chans=C, img=S).eval()
+    sampler = ClockSampler(cx.local)
+    if rank == 0:
+        sampler.start()
+    steps = max(3, args.steps)
+    tb = train_bench(cx, model, B, S, C, steps, GF[S]["train"])
+    clocks = sampler.stop() if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(cfgname)
+        if cfgname == "c3":
+            t = cpu["train_batch4_step"]
+            cpu = {"value": t["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": t["sample"]}
+    if rank == 0:
+        line = base_line(cx, cfgname, tb["value"], tb["ms_per_step"], steps, 3, clocks, cpu)
+        line["config"].update({"global_batch": world * B, "tokens_per_tile": (S // 14) ** 2 + 5,
+                               "parallelism": "batch-parallel x%d, NCCL all-reduce of the trainable gradients" % world,
+                               "gf_per_tile": GF[S]["train"]})
+        line["e2e"] = tb.pop("e2e")
+        line["gpu_launches"] = tb["gpu_launches_per_step"] * steps
+        pk = peaks()
+        line["roofline"] = {"bound": "tensor", "kernel": "whole training step (97 % of its FLOPs are bf16 tensor-core contractions)",
+                            "achieved": tb["tflops"] / world, "peak": pk["tc_sus"], "unit": "TFLOP/s",
+                            "frac": tb["tflops"] / world / pk["tc_sus"], "peak_kind": "sustained cuBLAS bf16 (kernel timed inside a long step)",
+                            "frac_of_burst": tb["tflops"] / world / pk["tc"], "traffic": None}
+        line["train"] = tb
+        print(json.dumps(line), flush=True)
+
+
+def run_c5(cx):
+    """whole-slide sweep: tiles live in HOST memory as raw uint8, loader worker processes fill the pinned ring"""
+    torch, args, dev, rank, world = cx.torch, cx.args, cx.dev, cx.rank, cx.world
+    from miphei_vit_b200 import wsi
+
+    B, S, n_tiles = args.batch or 64, 256, args.tiles
+    model = build_model(dev).eval()
+    eng = model.engine
+    base = synth_tiles_u8(torch, 256, S, 7).permute(0, 2, 3, 1).contiguous()   # 256 distinct tiles, cycled
+
+    class Slide:
+        def __len__(self):
+            return n_tiles
+
+        def __getitem__(self, i):
+            return base[i % 256]
+
+    tiles = Slide()
+    x_dev = normalize(torch, synth_tiles_u8(torch, B, S, 11 + rank)).to(dev)
+    for _ in range(3):
+        eng.infer(x_dev, reuse_output=True)
+    ms_res = cx.timed(lambda i: eng.infer(x_dev, reuse_output=True), max(3, min(args.steps, 10)))
+    wsi.infer_slide(model, tiles, batch=B, rank=rank, world=world * 8, num_workers=args.workers)  # warm-up: 1/8 of a shard
+    sampler = ClockSampler(cx.local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    n = wsi.infer_slide(model, tiles, batch=B, rank=rank, world=world, num_workers=args.workers)
+    e1.record()
+    cx.barrier()
+    wall = time.perf_counter() - t0
+    ms = cx.max_ms(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch_, om, cfg, sd, cores = _oracle()
+        v, k = cpu_forward(torch_, om, cfg, sd, 2, 3, 20.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "median of %d fp32 forward passes of batch 2 of the oracle port on %d threads" % (k, cores)}
+    if rank == 0:
+        nb = (n + B - 1) // B
+        line = base_line(cx, "c5", world * B / ms_res * 1e3, ms_res, max(3, min(args.steps, 10)), 3, clocks, cpu)
+        line["config"].update({"tiles": n_tiles, "batch": B, "loader_workers_per_gpu": args.workers,
+                               "parallelism": "tiles sharded round-robin x%d, no collective" % world, "gf_per_tile": GF[256]["fwd"]})
+        line["value_note"] = "forward at batch %d with inputs resident in HBM (per-GPU x N)" % B
+        line["e2e"] = {"value": n_tiles / ms * 1e3, "unit": UNIT, "ms_total": ms, "wall_s": wall,
+                       "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 16 * S * S),
+                       "api": "wsi.infer_slide(model, tiles): %d loader worker processes -> shared pinned ring -> "
+                              "engine.infer_stream (uint8 tiles normalised on the device, uint8 sink) -> host; the whole "
+                              "sweep of %d tiles (%d batches on rank 0) is one timed region, worker start-up included"
+                              % (args.workers, n_tiles, nb)}
+        line["gpu_launches"] = None
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -342,14 +627,25 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--tiles", type=int, default=4096)
+    ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    cx = Ctx(args)
+    if args.config == "c2":
+        run_c2(cx)
+    elif args.config in ("c3", "c4"):
+        run_train_config(cx, args.config)
     else:
-        run_cuda(args)
+        run_c5(cx)
+    cx.finish()
 
 
 if __name__ == "__main__":

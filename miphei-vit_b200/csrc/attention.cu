@@ -358,14 +358,13 @@ extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ld
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
   const CUtensorMap* tkv = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, p.kb);
   if (!tq || !tkv) return MV_ERR_ARG;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};  // one bit per device
+  if (first_use_on_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_fwd): %s", cudaGetErrorString(e));
       return (int)e;
     }
-    attr = true;
   }
   int grid = device_sms() > 0 ? device_sms() : 148;
   if (grid > p.total_tiles) grid = p.total_tiles;

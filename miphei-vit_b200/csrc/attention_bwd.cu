@@ -382,15 +382,14 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   const CUtensorMap* td64 = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 64);
   if (!tq || !td || !tq64 || !td64) return MV_ERR_ARG;
   const int smem = 2 * ATB_RTILE + 4 * ATB_CTILE + 128 + 4 * 64 * 4 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};  // one bit per device
+  if (first_use_on_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attn_bwd): %s", cudaGetErrorString(e));
       return (int)e;
     }
-    attr = true;
   }
   int grid = 2 * (device_sms() > 0 ? device_sms() : 148);  // two co-resident CTAs per SM
   if (grid > p.total_items) grid = p.total_items;

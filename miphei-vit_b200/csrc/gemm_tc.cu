@@ -989,15 +989,14 @@ static long long* g_gemm_prof = nullptr;  // diagnostics only (mv_gemm_set_profi
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
 static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};  // one bit per device: function attributes are per device
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE, PAIR, LIGHT>;
-  if (!attr_set) {
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm<%d,%d>): %s", BLOCK_N, MODE, cudaGetErrorString(e));
       return (int)e;
     }
-    attr_set = true;
   }
   const CUtensorMap* ta = nullptr;
   const CUtensorMap* ta2 = nullptr;

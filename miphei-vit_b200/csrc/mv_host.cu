@@ -14,8 +14,9 @@ namespace mv {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static int g_sms = 0;
-static int g_device = -1;
+// one process may drive several GPUs (one host thread each): everything device-specific is indexed by the CURRENT device
+constexpr int kMaxDevices = 64;
+static int g_sms[kMaxDevices] = {0};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -28,7 +29,16 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-int device_sms() { return g_sms; }
+static int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+int device_sms() { return g_sms[current_device()]; }
+bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  const uint64_t bit = 1ull << current_device();
+  return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("MV_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -83,13 +93,29 @@ struct TmapHash {
 };
 static std::mutex g_tmap_mu;
 static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> g_tmaps;
+constexpr size_t kTmapCacheMax = 65536;
+
+// Callers never hold pointers into the cache: every lookup hands out a COPY in a small thread-local ring (a launch takes
+// at most four descriptors and passes them to the kernel by value), so evicting cache entries under the lock is always safe.
+static const CUtensorMap* hand_out(const CUtensorMap* cached) {
+  static thread_local CUtensorMap ring[16];
+  static thread_local unsigned next = 0;
+  CUtensorMap* slot = &ring[next++ & 15u];
+  memcpy(slot, cached, sizeof(CUtensorMap));
+  return slot;
+}
+static void evict_if_full() {  // g_tmap_mu held
+  if (g_tmaps.size() <= kTmapCacheMax) return;
+  for (auto& kv : g_tmaps) free(kv.second);
+  g_tmaps.clear();
+}
 
 const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                     uint32_t box_cols) {
   TmapKey key{ptr, rows, cols, ld, box_rows, box_cols};
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   auto it = g_tmaps.find(key);
-  if (it != g_tmaps.end()) return it->second;
+  if (it != g_tmaps.end()) return hand_out(it->second);
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) {
     set_error("TMA operand must be 16-byte aligned with a 16-byte multiple pitch (ptr %p ld %llu)", ptr,
               (unsigned long long)ld);
@@ -109,12 +135,9 @@ const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t col
     free(mem);
     return nullptr;
   }
-  if (g_tmaps.size() > 65536) {  // unbounded growth guard: descriptors are tiny, but pointers may churn
-    for (auto& kv : g_tmaps) free(kv.second);
-    g_tmaps.clear();
-  }
+  evict_if_full();  // unbounded growth guard: descriptors are tiny, but operand pointers may churn
   g_tmaps.emplace(key, tm);
-  return tm;
+  return hand_out(tm);
 }
 
 const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, int c, int tw, int th, int stride) {
@@ -123,7 +146,7 @@ const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, 
               (uint32_t)th, (uint32_t)tw};
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   auto it = g_tmaps.find(key);
-  if (it != g_tmaps.end()) return it->second;
+  if (it != g_tmaps.end()) return hand_out(it->second);
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (c % 8)) {
     set_error("NHWC TMA source must be 16-byte aligned with C %% 8 == 0 (ptr %p C %d)", ptr, c);
     return nullptr;
@@ -143,8 +166,9 @@ const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, 
     free(mem);
     return nullptr;
   }
+  evict_if_full();
   g_tmaps.emplace(key, tm);
-  return tm;
+  return hand_out(tm);
 }
 
 }  // namespace mv
@@ -177,8 +201,7 @@ int mv_init(int device) {
     mv::set_error("cudaSetDevice: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  mv::g_sms = prop.multiProcessorCount;
-  mv::g_device = device;
+  if (device < mv::kMaxDevices) mv::g_sms[device] = prop.multiProcessorCount;
   if (!mv::g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -194,7 +217,7 @@ int mv_init(int device) {
 
 const char* mv_last_error(void) { return mv::g_err; }
 int mv_version(void) { return 100; }
-int mv_num_sms(void) { return mv::g_sms; }
+int mv_num_sms(void) { return mv::device_sms(); }
 int64_t mv_launch_count(void) { return mv::g_launches.load(); }
 void mv_reset_launch_count(void) { mv::g_launches.store(0); }
 

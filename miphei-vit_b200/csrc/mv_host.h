@@ -5,17 +5,23 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/miphei_b200.h"
 
 namespace mv {
 
 void set_error(const char* fmt, ...);
-int device_sms();
+int device_sms();  // SM count of the CURRENT device (0 before mv_init on it)
 void count_launch(int n = 1);
+// true the first time it is called on the current device for this flag word — per-device one-time setup such as
+// cudaFuncSetAttribute (function attributes are per device; a process may drive several GPUs)
+bool first_use_on_device(std::atomic<uint64_t>& mask);
 
 // 2-D bf16 row-major tensor map: inner extent `cols` (elements), outer extent `rows`, row pitch `ld` elements.
 // Box = box_cols x box_rows, 128-byte swizzle (box_cols * 2 bytes must be 128), OOB reads return zeros.
-// Cached by (ptr, rows, cols, ld, box); returns nullptr and sets the error string on failure.
+// Cached by (ptr, rows, cols, ld, box); returns nullptr and sets the error string on failure. The returned pointer is a
+// thread-local COPY valid until the calling thread's 16th following lookup (pass it to the kernel by value).
 const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                     uint32_t box_cols = 64);
 // 4-D NHWC bf16 map [B, H, W, C] with box {64 channels, tw*stride, th*stride, 1} traversed with element stride

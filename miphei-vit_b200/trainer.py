@@ -271,42 +271,3 @@ class Trainer:
                     works.append(self._allreduce(coll))
         self._after_step()
         return self.loss_buf
-
-
-def bench_train(model, args, rank, world, dev):
-    """BASELINE configs[2]: training step (fwd + bwd + loss + clip + Adam), batch 32 per GPU, weak scaling."""
-    if getattr(args, "no_train", False):
-        return None
-    import torch
-
-    B = getattr(args, "train_batch", 32)
-    S = 256
-    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
-    x = torch.randn((B, 3, S, S), generator=g).to(dev)
-    y = (torch.empty((B, 16, S, S)).exponential_(1.0 / 20.0, generator=g).clamp_(0, 255).floor_() / 255.0 * 1.8 - 0.9).to(dev)
-    w = torch.linspace(1.0, 10.6, 16)
-    tr = Trainer(model, marker_weights=w, batch_size=B, total_steps=10000)
-    steps = max(3, min(args.steps, 10))
-    for _ in range(3):
-        tr.step(x, y)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = tr.step(x, y)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    model.eval()
-    return {"metric": "tiles_per_sec_train_256px_16ch", "value": world * B / ms * 1e3, "unit": "tiles/s",
-            "ms_per_step": ms, "steps": steps, "batch_per_gpu": B, "loss": float(loss.item()),
-            "tflops": world * B * 1633.87 / ms, "scaling": "weak",
-            "note": "fwd+bwd+WeightedMSE+clip+Adam, every kernel hand-written (encoder, decoder with train-mode BatchNorm, "
-                    "loss, optimiser); NCCL AVG all-reduce of 26.8 MB in 2 buckets overlapped with the encoder backward"}
