@@ -117,7 +117,12 @@ typedef struct mv_gemm_args {
                          The training-mode decoder keeps feature maps and conv weights in fp16: the
                          reference trains under fp16 autocast (configs/config.yaml:23) and the LoRA gradients need the
                          extra mantissa bits. Outputs are unaffected. */
-  int32_t reserved3;
+  int32_t reserved3;  /* stream-K policy: 0 = when worthwhile, 1 = whenever legal, 2 = never */
+  void* workspace;    /* optional, 256-byte aligned, ZERO-INITIALISED ONCE by the caller and then left to the library (it
+                         restores the zeros): lets LINEAR / SWIGLU / SWIGLU_BWD GEMMs spread the k blocks of their last,
+                         partial wave of tiles over all SMs (stream-K; partial sums meet here). One workspace per stream:
+                         two GEMMs that may run concurrently must not share it. >= 20 MB covers every shape; NULL disables. */
+  int64_t workspace_bytes;
 } mv_gemm_args;
 
 int mv_gemm_bf16(const mv_gemm_args* args, void* stream);

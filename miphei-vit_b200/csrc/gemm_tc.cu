@@ -67,7 +67,66 @@ struct GemmDev {
   long long* prof;
   int kskip0, kskip1;  // k blocks [kskip0, kskip1) are skipped (their B columns are zero)
   uint32_t idesc_clear;  // instruction-descriptor format bits to clear: bit 7 (A is fp16, not bf16), bit 10 (B is fp16)
+  // Stream-K for the last, partial wave of tiles (sk_rem > 0): tiles [0, sk_dp) run whole, round-robin over the scheduling
+  // units (CTAs / CTA pairs); the k blocks of the remaining sk_rem tiles are divided evenly over ALL units. Partial
+  // accumulators of a tile meet in its fp32 workspace slot (vector red.add at L2); the contributor that arrives last
+  // (sk_cnt) reads the sums back, zeroes the slot for the next launch and runs the ordinary epilogue. Nobody waits.
+  int sk_dp, sk_rem;
+  float* sk_ws;
+  int* sk_cnt;
 };
+
+__host__ __device__ constexpr bool gemm_sk_mode(int mode, int block_n) {
+  return (mode == MV_GEMM_LINEAR && block_n >= 32) || mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD;
+}
+
+// The sequence of (tile, k-block range) segments of one scheduling unit — identical in the producer, the MMA issuer and
+// the epilogue warps. Whole tiles first (split-K "tiles" of MV_GEMM_NN_ATOMIC included), then this unit's share of the
+// stream-K remainder, cut at tile boundaries.
+struct SegIter {
+  int units, num_mn, splits, nkb, dp_end, sk_dp;
+  int tile_next;
+  long long k_cur, k_hi;
+  __device__ SegIter(const GemmDev& p, int unit, int units_) {
+    units = units_;
+    num_mn = p.num_m_blocks * p.num_n_blocks;
+    splits = p.splits;
+    nkb = p.num_k_blocks;
+    sk_dp = p.sk_dp;
+    dp_end = p.sk_rem > 0 ? p.sk_dp : num_mn * splits;
+    tile_next = unit;
+    const long long wk = (long long)p.sk_rem * nkb;
+    k_cur = wk * unit / units;
+    k_hi = wk * (unit + 1) / units;
+  }
+  __device__ bool next(int& tile, int& kb0, int& kb1, bool& partial) {
+    if (tile_next < dp_end) {
+      tile = tile_next;
+      tile_next += units;
+      const int split = tile / num_mn;
+      kb0 = (int)((long long)nkb * split / splits);
+      kb1 = (int)((long long)nkb * (split + 1) / splits);
+      partial = false;
+      return true;
+    }
+    if (k_cur < k_hi) {
+      const int r = (int)(k_cur / nkb);
+      kb0 = (int)(k_cur - (long long)r * nkb);
+      const long long left = k_hi - k_cur;
+      const int len = left < (long long)(nkb - kb0) ? (int)left : nkb - kb0;
+      kb1 = kb0 + len;
+      tile = sk_dp + r;
+      partial = len != nkb;
+      k_cur += len;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void red_add_v4(float4* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // PAIR: cta_group::2 — two CTAs of a cluster share one 256 x BLOCK_N tile; each stages its own 128 A rows and HALF of
 // the B rows (the tensor core reads the other half from the peer's shared memory), halving B traffic per SM.
@@ -244,19 +303,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   const int num_mn = p.num_m_blocks * p.num_n_blocks;
-  const int num_tiles = num_mn * p.splits;
-  const int nkb_total = p.num_k_blocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
-        const int split = tile / num_mn, mn = tile - split * num_mn;
+      SegIter it(p, tile_start, tile_step);
+      int tile, kb0, kb1;
+      bool partial;
+      while (it.next(tile, kb0, kb1, partial)) {
+        const int mn = tile % num_mn;
         const int m_blk = PAIR ? (mn % p.num_m_blocks) * 2 + (int)cta_rank : mn % p.num_m_blocks;  // 128-row block
         const int n_blk = mn / p.num_m_blocks;
-        const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
         const int m0 = m_blk * GEMM_BLOCK_M;
         int brow[2];
         if (MODE == MV_GEMM_SWIGLU) {  // 128 gate rows + the matching 128 value rows
@@ -391,9 +450,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint64_t db0 = MODE == MV_GEMM_NN_ATOMIC
                                ? umma_desc_sw128(smem_base + Cfg::kABytes, 1024, 8192)  // MN-major: 64-column atoms 8 KB apart
                                : umma_desc_sw128(smem_base + Cfg::kABytes);
-      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
-        const int split = tile / num_mn;
-        const int kb0 = (int)((long long)nkb_total * split / p.splits), kb1 = (int)((long long)nkb_total * (split + 1) / p.splits);
+      SegIter it(p, tile_start, tile_step);
+      int tile, kb0, kb1;
+      bool partial;
+      while (it.next(tile, kb0, kb1, partial)) {
         long long t0_ = (kProf && p.prof) ? clock64() : 0;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         if (kProf && p.prof) prof_acc[2] += clock64() - t0_;
@@ -458,7 +518,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int i = ep_tid; i < 2 * BLOCK_N; i += EPT) cstat[i] = 0.f;
       ep_bar();
     }
-    for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
+    __shared__ int sk_last;
+    SegIter it(p, tile_start, tile_step);
+    int tile, kb0_, kb1_;
+    bool partial;
+    while (it.next(tile, kb0_, kb1_, partial)) {
       const int mn = tile % num_mn;
       const int m_blk = PAIR ? (mn % p.num_m_blocks) * 2 + (int)cta_rank : mn % p.num_m_blocks;  // 128-row block
       const int n_blk = mn / p.num_m_blocks;
@@ -553,6 +617,69 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const long long te1_ = (kProf && p.prof) ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
+      // ---- stream-K segment of a remainder tile: add the partial accumulators to the tile's workspace slot; only the
+      // contributor that arrives last goes on to the epilogue, reading the sums back instead of TMEM
+      bool from_ws = false;
+      float4* ws4 = nullptr;
+      if constexpr (gemm_sk_mode(MODE, BLOCK_N) && !LIGHT) {
+        if (partial) {
+          const int slot = (tile - p.sk_dp) * (PAIR ? 2 : 1) + (int)cta_rank;
+          ws4 = reinterpret_cast<float4*>(p.sk_ws) + (size_t)slot * (BLOCK_N / 4) * 128;
+#pragma unroll 1
+          for (int c = egrp; c < BLOCK_N / 32; c += EGRPS) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            float4* pp = ws4 + (size_t)(c * 8) * 128 + row_in_tile;  // [column / 4][row][4]: a warp's 32 rows are contiguous
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red_add_v4(pp + q * 128, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {  // the accumulator stage is free again
+            if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+          }
+          __threadfence();
+          ep_bar();
+          if (ep_tid == 0) {
+            // contributors of this tile = units whose k range meets [r nkb, (r + 1) nkb)  (ranges: [wk u / U, wk (u + 1) / U))
+            const long long nkb = p.num_k_blocks, wk = (long long)p.sk_rem * nkb, U = tile_step;
+            const long long s0 = (long long)(tile - p.sk_dp) * nkb, e0 = s0 + nkb;
+            const int ua = (int)(((s0 + 1) * U + wk - 1) / wk) - 1, ub = (int)((e0 * U + wk - 1) / wk) - 1;
+            const int n_contrib = ub - ua + 1;
+            const int old = atomicAdd(p.sk_cnt + slot, 1);
+            const int last = old == n_contrib - 1;
+            if (last) p.sk_cnt[slot] = 0;  // ready for the next launch
+            sk_last = last;
+          }
+          ep_bar();
+          const bool last = sk_last != 0;
+          ep_bar();  // sk_last may be rewritten by the next segment only after everyone has read it
+          if (!last) {
+            if (++as == 2) { as = 0; aphase ^= 1; }
+            continue;
+          }
+          __threadfence();
+          from_ws = true;
+        }
+      }
+      // accumulator chunk source of the epilogues below: TMEM, or (stream-K finisher) the summed workspace slot, which is
+      // zeroed as it is read
+      auto acc_ld32 = [&](int col0, uint32_t (&v)[32]) {
+        if (!(gemm_sk_mode(MODE, BLOCK_N) && !LIGHT) || !from_ws) {
+          tmem_ld32(taddr + col0, v);
+          return;
+        }
+        float4* pp = ws4 + (size_t)(col0 / 4) * 128 + row_in_tile;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldcg(pp + q * 128);
+          __stcg(pp + q * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+          v[4 * q] = __float_as_uint(t.x); v[4 * q + 1] = __float_as_uint(t.y);
+          v[4 * q + 2] = __float_as_uint(t.z); v[4 * q + 3] = __float_as_uint(t.w);
+        }
+      };
+      auto acc_wait = [&]() { if (!(gemm_sk_mode(MODE, BLOCK_N) && !LIGHT) || !from_ws) tmem_ld_wait(); };
 
       if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
         // TMEM (one row per lane) -> padded smem tile -> row-contiguous global accesses (coalesced residual read,
@@ -562,7 +689,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
         constexpr int NC = BLOCK_N / 32;
         uint32_t v[32];
-        tmem_ld32(taddr + egrp * 32, v);
+        acc_ld32(egrp * 32, v);
 #pragma unroll 1
         for (int c = egrp; c < NC; c += EGRPS) {
           // GATE_MASK: the per-(row, head) gate gradients of this chunk, fetched before the TMEM wait (hidden latency)
@@ -583,11 +710,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 du4[it] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nnm >> 4)]);
             }
           }
-          tmem_ld_wait();
+          acc_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (c + EGRPS < NC) tmem_ld32(taddr + (c + EGRPS) * 32, v);
+          if (c + EGRPS < NC) acc_ld32((c + EGRPS) * 32, v);
           float4 q_[8];
           if (p.out_f32) {  // residual of this chunk was prefetched; start fetching the next chunk's now
 #pragma unroll
@@ -751,9 +878,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
         for (int c = egrp; c < 4; c += EGRPS) {
           uint32_t g[32], u[32];
-          tmem_ld32(taddr + c * 32, g);
-          tmem_ld32(taddr + 128 + c * 32, u);
-          tmem_ld_wait();
+          acc_ld32(c * 32, g);
+          acc_ld32(128 + c * 32, u);
+          acc_wait();
           const int j0 = n_blk * 128 + c * 32;
           float fg[32], fv[32], fo[32];
 #pragma unroll
@@ -909,8 +1036,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
         for (int c = egrp; c < BLOCK_N / 32; c += EGRPS) {
           uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
+          acc_ld32(c * 32, v);
+          acc_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -951,7 +1078,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !from_ws) {  // (a stream-K finisher released its accumulator stage before the counter)
         if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
       }
       if (kProf && p.prof && warp == 2) {
@@ -1062,16 +1189,38 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.conv_cb1 = (a.conv_c1 + 63) / 64;
 
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
-  int grid = device_sms() > 0 ? device_sms() : 148;
+  const int sms = device_sms() > 0 ? device_sms() : 148;
+  int grid = sms;
+  if (PAIR) grid &= ~1;
+  if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
+  const int units_full = PAIR ? grid / 2 : grid;
+  // ---- stream-K for the partial last wave (see GemmDev): needs a caller-provided zeroed workspace
+  p.sk_dp = tiles;
+  p.sk_rem = 0;
+  p.sk_ws = nullptr;
+  p.sk_cnt = nullptr;
+  static const int sk_env = [] { const char* e = getenv("MV_GEMM_SK"); return e ? atoi(e) : 1; }();  // 0 off, 1 auto, 2 always
+  if (gemm_sk_mode(MODE, BLOCK_N) && !LIGHT && sk_env != 0 && a.reserved3 != 2 && a.workspace && !a.conv && !a.colstats && a.rows_per_group == 0 &&
+      a.kskip_end == 0 && p.splits == 1 && (reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0) {
+    const int rem = tiles % units_full;
+    const long long wk = (long long)rem * p.num_k_blocks;
+    const long long need = 4096 + (long long)rem * (PAIR ? 2 : 1) * 128 * BLOCK_N * 4;
+    // worth it when the last wave leaves a good part of the machine idle and every unit still gets a few k blocks
+    const bool worth = sk_env == 2 || a.reserved3 == 1 || (rem * 100 <= units_full * 85 && wk >= 2ll * units_full);
+    if (rem > 0 && wk >= units_full && worth && need <= a.workspace_bytes && rem * (PAIR ? 2 : 1) <= 1024) {
+      p.sk_dp = tiles - rem;
+      p.sk_rem = rem;
+      p.sk_cnt = reinterpret_cast<int*>(a.workspace);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + 4096);
+    }
+  }
   if (PAIR) {
-    grid &= ~1;
-    if (2 * tiles < grid) grid = 2 * tiles;
+    if (p.sk_rem == 0 && 2 * tiles < grid) grid = 2 * tiles;
     (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE, BLOCK_N, LIGHT)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, p);
     MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
     return MV_OK;
   }
-  if (LIGHT) grid *= 2;  // two co-resident CTAs per SM
-  if (tiles < grid) grid = tiles;
+  if (p.sk_rem == 0 && tiles < grid) grid = tiles;
   MV_LAUNCH(kern, grid, gemm_threads(MODE, BLOCK_N, LIGHT), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;

@@ -39,6 +39,7 @@ class GemmArgs(ctypes.Structure):
         ("colstats", c_void_p),
         ("kskip_begin", c_i32), ("kskip_end", c_i32),
         ("ab_f16", c_i32), ("reserved3", c_i32),
+        ("workspace", c_void_p), ("workspace_bytes", c_i64),
     ]
 
 

@@ -36,10 +36,27 @@ def _rowmajor(t, name):
     return t
 
 
+_SK_BYTES = 20 * 1024 * 1024 + 4096
+_sk_workspaces = {}
+
+
+def _sk_workspace(device):
+    """stream-K workspace of the CURRENT stream on this device (zeroed once; the kernels keep it zero between launches).
+    Keyed by stream: GEMMs that can run concurrently never share one."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _sk_workspaces.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # never allocate inside a graph capture: warm-up runs create the workspace of a capture stream
+        ws = torch.zeros(_SK_BYTES, dtype=torch.uint8, device=device)
+        _sk_workspaces[key] = ws
+    return ws
+
+
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
          resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False, pair=0,
-         kskip=None):
+         kskip=None, stream_k=True):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
     lib = _lib_for(a)
     # 16-bit operands: bf16 (default) or fp16 (training-mode decoder maps / weights); the formats are independent
@@ -135,6 +152,11 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
     # both tensor-core operands must share one format (a mixed descriptor is an illegal instruction on sm_100a)
     assert a.dtype == b.dtype and (a2t is None or a2t.dtype == a.dtype), (a.dtype, b.dtype)
     args.ab_f16 = 3 if a.dtype == torch.float16 else 0
+    if mode in (GEMM_LINEAR, GEMM_SWIGLU, GEMM_SWIGLU_BWD) and conv is None and M >= 1024 and stream_k:
+        ws = _sk_workspace(a.device)
+        if ws is not None:
+            args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+            args.reserved3 = 1 if stream_k == "force" else 0
     if kskip is not None:  # K range with all-zero B columns: never loaded
         args.kskip_begin, args.kskip_end = int(kskip[0]), int(kskip[1])
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")

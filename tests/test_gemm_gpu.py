@@ -151,3 +151,48 @@ def test_gemm_cta_pair_swiglu():
     d1 = ops.gemm(dy, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=h1, pair=1)
     d2 = ops.gemm(dy, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=h1, pair=2)
     assert torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("M,N,K", [(5264, 1536, 1536), (5264, 4608, 1536), (5264, 1536, 4096), (10528, 1536, 1536), (2000, 768, 512),
+                                   (1300, 1536, 256)])
+def test_gemm_stream_k_matches_whole_tile_schedule(M, N, K):
+    """the last partial wave of tiles split along K over all SMs (partials reduced at L2, last arriver runs the epilogue)
+    gives the same result as the whole-tile schedule — fp32 reassociation only — launch after launch (the workspace is
+    restored to zero by the kernel itself), for every fused epilogue that uses it"""
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    b = _rand((N, K), 0.05, 2).bfloat16()
+    scale, shift, resid = _rand((N,), 1.0, 3), _rand((N,), 1.0, 4), _rand((M, N), 1.0, 5)
+    ref = (a.float() @ b.float().t()) * scale + shift + resid
+    base = ops.gemm(a, b, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, stream_k=False)
+    for _ in range(3):
+        out = ops.gemm(a, b, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, stream_k="force")
+        _close(out, ref, 2e-5)
+        assert (out - base).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    outb = ops.gemm(a, b, shift=shift, stream_k="force")
+    _close(outb, a.float() @ b.float().t() + shift, 1e-2)
+    ws = ops._sk_workspace(a.device)
+    assert ws is not None and int(ws.count_nonzero()) == 0          # zeros restored, counters back to 0
+
+
+def test_gemm_stream_k_swiglu_fwd_bwd():
+    ops = _ops()
+    M, D, H = 5264, 1536, 1024
+    x = _rand((M, D), 1.0, 1).bfloat16()
+    w1 = _rand((2 * H, D), 0.03, 2).bfloat16()
+    b1 = _rand((2 * H,), 0.1, 3)
+    aux0 = torch.empty((M, 2 * H), dtype=torch.bfloat16, device="cuda")
+    aux1 = torch.empty_like(aux0)
+    u0 = ops.gemm(x, w1, mode=ops.GEMM_SWIGLU, shift=b1, aux=aux0, stream_k=False)
+    u1 = ops.gemm(x, w1, mode=ops.GEMM_SWIGLU, shift=b1, aux=aux1, stream_k="force")
+    h = x.float() @ w1.float().t() + b1
+    ref = torch.nn.functional.silu(h[:, :H]) * h[:, H:]
+    _close(u1, ref, 1.5e-2)
+    assert (u1.float() - u0.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (aux1.float() - aux0.float()).abs().max().item() <= 2e-2 * h.abs().max().item()
+    w2t = _rand((H, D), 0.03, 5).bfloat16()          # dU = dX . W2^T: [M, D] x [H, D]^T
+    dx = _rand((M, D), 1.0, 6).bfloat16()
+    g0 = ops.gemm(dx, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=aux0, stream_k=False)
+    g1 = ops.gemm(dx, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=aux0, stream_k="force")
+    assert (g1.float() - g0.float()).abs().max().item() <= 2e-2 * g0.float().abs().max().item()
+    assert int(ops._sk_workspace(x.device).count_nonzero()) == 0

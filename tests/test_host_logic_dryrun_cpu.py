@@ -37,6 +37,7 @@ def stubbed(monkeypatch):
     monkeypatch.setattr(ops, "_lib_for", lambda t: stub)
     monkeypatch.setattr(ops, "require_cuda", lambda device, what: None)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_sk_workspace", lambda device: None)
     return stub
 
 
