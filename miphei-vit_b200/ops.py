@@ -56,8 +56,10 @@ def _sk_workspace(device):
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
          resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False, pair=0,
-         kskip=None, stream_k=True):
-    """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h."""
+         kskip=None, stream_k=False):
+    """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h.
+    stream_k: False (default) | True (when the library judges it worthwhile) | "force" — measured slower on every encoder
+    shape (the L2 reduction of the partial tiles costs more than the idle last wave), kept for small grids."""
     lib = _lib_for(a)
     # 16-bit operands: bf16 (default) or fp16 (training-mode decoder maps / weights); the formats are independent
     assert a.dtype in _H16 and b.dtype in _H16

@@ -33,6 +33,16 @@ def _worker(rank, world, port, q):
         for _, p in flat.order:
             assert p.data.untyped_storage().data_ptr() == flat.flat.untyped_storage().data_ptr()
             assert p.grad.untyped_storage().data_ptr() == flat.gflat.untyped_storage().data_ptr()
+        # the LoRA segment is laid out block by block, 32 * D floats each: the trainer reduces it in block-range slices
+        # (upper half of the blocks while the lower half is still in backward) and mv_lora_refresh reads it that way
+        D, off = 128, flat.n_dec
+        offsets = {}
+        for n, p in flat.order:
+            offsets[n] = (p.data.data_ptr() - flat.flat.data_ptr()) // 4
+        for i in range(2):
+            for j, t in enumerate(("lora_q.A", "lora_q.B", "lora_v.A", "lora_v.B")):
+                assert offsets["encoder.vit.blocks.%d.attn.qkv.%s" % (i, t)] == off + i * 32 * D + j * 8 * D
+        assert flat.total == off + 2 * 32 * D
         # rank-dependent fake gradients -> bucketed AVG all-reduce -> identical on both ranks, equal to the mean
         g = torch.Generator().manual_seed(100 + rank)
         flat.gflat.copy_(torch.randn(flat.total, generator=g))
