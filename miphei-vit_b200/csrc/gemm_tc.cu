@@ -14,6 +14,9 @@
 
 namespace mv {
 
+// internal mode (never passed through the C ABI): LINEAR with fp32 output + fp32 residual whose epilogue moves the residual in
+// and the result out with TMA (bulk async copies through swizzled shared-memory tiles) instead of per-thread ld / st
+constexpr int MV_GEMM_LINEAR_TMA = 16;
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
@@ -140,11 +143,17 @@ struct GemmCfg {
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = gemm_epi_warps(MODE, BLOCK_N, LIGHT);
-  static constexpr int kStagingBytes = kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
+  static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA;
+  // LINEAR_TMA: per epilogue warp kTmaResStages residual tiles + kTmaOutStages output tiles of 32 rows x 32 fp32 columns
+  // (4 KB each, 128-byte swizzle, 1 KB aligned) directly behind the operand ring; the transpose staging is not needed there
+  static constexpr int kTmaResStages = 2, kTmaOutStages = 1;
+  static constexpr int kEpiTmaBytes = kEpiTma ? kEpiWarps * (kTmaResStages + kTmaOutStages) * 4096 : 0;
+  static constexpr int kStagingBytes = kEpiTma ? 0 : kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
   // LINEAR: per-epilogue-warp copy of the tile's (scale, shift) columns, staged before the accumulator is awaited
-  static constexpr int kCoefBytes = (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) ? kEpiWarps * 2 * BLOCK_N * 4 : 0;
-  static constexpr int kFixedBytes = 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes + kStatBytes + kCoefBytes;
+  static constexpr int kCoefBytes = ((MODE == MV_GEMM_LINEAR || kEpiTma) && BLOCK_N >= 32) ? kEpiWarps * 2 * BLOCK_N * 4 : 0;
+  static constexpr int kBarBytes = 512;  // mbarriers: ring + accumulator stages in the first 256 B, TMA-epilogue barriers behind
+  static constexpr int kFixedBytes = 1024 /*align*/ + kBarBytes + kEpiTmaBytes + kStagingBytes + kStatBytes + kCoefBytes;
   static constexpr int kRingBudget = 227 * 1024 - kFixedBytes;
   static constexpr int kStagesDeep = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kStages = !LIGHT ? kStagesDeep : (BLOCK_N <= 32 ? 4 : BLOCK_N <= 64 ? 3 : 2);
@@ -154,7 +163,9 @@ struct GemmCfg {
   static constexpr int kTmemCols = MODE == MV_GEMM_HEAD_CONV ? 512
                                    : kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static constexpr int kRingEnd = kStages * kStageBytes + kEpiTmaBytes;  // barriers start here
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(!kEpiTma || (kStageBytes % 1024 == 0 && BLOCK_N % 32 == 0), "TMA epilogue tiles must stay 1 KB aligned");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -239,7 +250,8 @@ __device__ __forceinline__ void epilogue_linear_chunk(const GemmDev& p, const ui
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
 __global__ void __launch_bounds__(gemm_threads(MODE, BLOCK_N, LIGHT), LIGHT ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
+                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_r,
+                    const __grid_constant__ CUtensorMap tmap_o, const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
   constexpr int STAGES = Cfg::kStages;
   unsigned long long prof_ns0 = 0;
@@ -251,7 +263,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  const uint32_t bar_base = smem_base + Cfg::kRingEnd;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -259,12 +271,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::kStageBytes + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kRingEnd + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  float* staging_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::kStageBytes + 256);
-  float* cstat = staging_all + Cfg::kEpiWarps * 32 * 36;  // [2][256]
+  float* staging_all = reinterpret_cast<float*>(smem_gen + Cfg::kRingEnd + Cfg::kBarBytes);
+  float* cstat = staging_all + Cfg::kStagingBytes / 4;  // [2][256]
   float* coef_all = cstat + 2 * 256;                      // [epilogue warp][scale BLOCK_N | shift BLOCK_N]
 
   if (warp == 0 && lane == 0) {
@@ -281,6 +293,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(tfull_bar(s), 1);
       // one arrival per epilogue warp (pair: the peer's warps arrive remotely)
       mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * Cfg::kEpiWarps);
+    }
+    if constexpr (Cfg::kEpiTma) {
+#pragma unroll
+      for (int i = 0; i < Cfg::kEpiWarps * Cfg::kTmaResStages; ++i) mbar_init(bar_base + 256u + 8u * i, 1);
+      tma_prefetch_desc(&tmap_r);
+      tma_prefetch_desc(&tmap_o);
     }
     fence_barrier_init();
   }
@@ -519,6 +537,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       ep_bar();
     }
     __shared__ int sk_last;
+    // LINEAR_TMA: this warp's residual / output tiles and residual barriers; running chunk counters give stage and parity
+    constexpr int TR = Cfg::kTmaResStages, TO = Cfg::kTmaOutStages;
+    const uint32_t tma_epi_base = smem_base + STAGES * Cfg::kStageBytes + (uint32_t)ew * (TR + TO) * 4096u;
+    uint8_t* tma_epi_gen = smem_gen + STAGES * Cfg::kStageBytes + (size_t)ew * (TR + TO) * 4096;
+    auto rbar = [&](int s_) { return bar_base + 256u + 8u * (uint32_t)(ew * TR + s_); };
+    uint32_t tma_issued = 0, tma_waited = 0;
     SegIter it(p, tile_start, tile_step);
     int tile, kb0_, kb1_;
     bool partial;
@@ -559,7 +583,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       float* coef = coef_all + ew * (2 * BLOCK_N);
-      if constexpr (MODE == MV_GEMM_LINEAR && BLOCK_N >= 32) {
+      if constexpr ((MODE == MV_GEMM_LINEAR || MODE == MV_GEMM_LINEAR_TMA) && BLOCK_N >= 32) {
         // this tile's (scale, shift) columns -> warp-private smem, also ahead of the accumulator wait
 #pragma unroll
         for (int i = lane * 4; i < BLOCK_N; i += 128) {
@@ -572,7 +596,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           *reinterpret_cast<float4*>(coef + i) = sc;
           *reinterpret_cast<float4*>(coef + BLOCK_N + i) = sh;
         }
-        if (p.out_f32) load_resid(egrp, qn);
+        if constexpr (MODE == MV_GEMM_LINEAR) {
+          if (p.out_f32) load_resid(egrp, qn);
+        }
         __syncwarp();
       }
       // SWIGLU_BWD: the saved pre-activations [g | v] of a 32-column chunk (4 row groups per lane), fetched one chunk
@@ -610,6 +636,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 du_tile[c][it] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in2)[(long long)mm * p.ldin2 + (nnm >> 4)]);
             }
           }
+        }
+      }
+      // LINEAR_TMA: residual tiles of the first chunks are requested before the accumulator is awaited
+      auto issue_res = [&](int chunk) {
+        const uint32_t s_ = tma_issued % TR;
+        ++tma_issued;
+        mbar_expect_tx(rbar(s_), 4096u);
+        tma_load_2d(tma_epi_base + s_ * 4096u, &tmap_r, rbar(s_), n_blk * BLOCK_N + chunk * 32, m_blk * GEMM_BLOCK_M + quad * 32);
+      };
+      if constexpr (MODE == MV_GEMM_LINEAR_TMA) {
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < TR && c < BLOCK_N / 32; ++c) issue_res(c);
         }
       }
       const long long te0_ = (kProf && p.prof) ? clock64() : 0;
@@ -839,6 +878,56 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           __syncwarp();
+        }
+      } else if constexpr (MODE == MV_GEMM_LINEAR_TMA) {
+        // x_out = acc * scale + shift + residual, fp32, 32 rows x 32 columns per step and warp.  The accumulator arrives one
+        // row per lane (tcgen05.ld 32x32b); the residual tile sits in shared memory in the 128-byte-swizzled layout TMA
+        // wrote (16-byte chunk j of row r at r * 128 + ((j ^ (r & 7)) << 4)), which a row-per-lane reader walks without bank
+        // conflicts; the result goes back through the same layout and one TMA store. No per-thread global access at all:
+        // the bytes in flight are set by the bulk copies, not by how many loads four warps can keep outstanding.
+        constexpr int NC = BLOCK_N / 32;
+        const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
+        const int swz = lane & 7;
+        uint32_t v[32];
+        acc_ld32(0, v);
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          acc_wait();
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+          if (c + 1 < NC) acc_ld32((c + 1) * 32, v);
+          const uint32_t s_ = tma_waited % TR;
+          mbar_wait(rbar(s_), (tma_waited / TR) & 1u);
+          ++tma_waited;
+          const uint8_t* rs = tma_epi_gen + s_ * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rs + ((j ^ swz) << 4));
+            const float4 sc = *reinterpret_cast<const float4*>(coef + c * 32 + 4 * j);            // same address in every lane:
+            const float4 sh = *reinterpret_cast<const float4*>(coef + BLOCK_N + c * 32 + 4 * j);  // shared-memory broadcast
+            a[4 * j + 0] = fmaf(a[4 * j + 0], sc.x, sh.x) + r4.x;
+            a[4 * j + 1] = fmaf(a[4 * j + 1], sc.y, sh.y) + r4.y;
+            a[4 * j + 2] = fmaf(a[4 * j + 2], sc.z, sh.z) + r4.z;
+            a[4 * j + 3] = fmaf(a[4 * j + 3], sc.w, sh.w) + r4.w;
+          }
+          fence_proxy_async_smem();  // our generic reads of the residual stage precede the async-proxy refill below
+          __syncwarp();
+          if (lane == 0) {
+            if (c + TR < NC) issue_res(c + TR);
+            tma_store_wait_read<TO - 1>();  // the store that last used this output stage has drained its shared-memory source
+          }
+          __syncwarp();
+          uint8_t* os = tma_epi_gen + (TR + (c % TO)) * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(os + ((j ^ swz) << 4)) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          fence_proxy_async_smem();  // generic writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_o, tma_epi_base + (TR + (c % TO)) * 4096u, n_blk * BLOCK_N + c * 32, m_warp);
+            tma_store_commit();
+          }
         }
       } else if constexpr (MODE == MV_GEMM_LINEAR) {
         constexpr int CH = 16;
@@ -1089,6 +1178,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (MODE == MV_GEMM_LINEAR && p.colstats && stat_nblk >= 0) flush_stats(stat_nblk);
+    if constexpr (MODE == MV_GEMM_LINEAR_TMA) {
+      if (lane == 0) tma_store_wait<0>();  // every output tile has landed before the CTA retires
+    }
   }
 
   if (kProf && p.prof && lane == 0 && warp <= 2) {
@@ -1149,6 +1241,13 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   } else {
     ta = get_tmap_2d_bf16(a.a, a.m, a.k, a.lda, GEMM_BLOCK_M);
     ta2 = ta;
+  }
+  const CUtensorMap* tr = ta;  // residual / output maps of the TMA epilogue (dummies elsewhere)
+  const CUtensorMap* to = ta;
+  if (MODE == MV_GEMM_LINEAR_TMA) {
+    tr = get_tmap_2d_f32(a.resid, a.m, a.n, a.ldr, 32);
+    to = get_tmap_2d_f32(a.out, a.m, a.n, a.ldo, 32);
+    if (!tr || !to) return MV_ERR_ARG;
   }
   const CUtensorMap* tb = tb_conv ? tb_conv
                           : MODE == MV_GEMM_NN_ATOMIC ? get_tmap_2d_bf16(a.b, a.k, a.n, a.ldb, 64)
@@ -1216,12 +1315,12 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   }
   if (PAIR) {
     if (p.sk_rem == 0 && 2 * tiles < grid) grid = 2 * tiles;
-    (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE, BLOCK_N, LIGHT)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, p);
+    (void)launch_pdl(kern, dim3(grid), dim3(gemm_threads(MODE, BLOCK_N, LIGHT)), (size_t)Cfg::kSmemBytes, stream, 2, *ta, *ta2, *tb, *tr, *to, p);
     MV_CHECK_LAUNCH("gemm_bf16_tc_pair");
     return MV_OK;
   }
   if (p.sk_rem == 0 && tiles < grid) grid = tiles;
-  MV_LAUNCH(kern, grid, gemm_threads(MODE, BLOCK_N, LIGHT), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, p);
+  MV_LAUNCH(kern, grid, gemm_threads(MODE, BLOCK_N, LIGHT), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, *tr, *to, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
 }
@@ -1346,7 +1445,14 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
       }
       if (use_pair && bn == 192) return launch_gemm<192, MV_GEMM_LINEAR, true>(a, stream);
       if (bn == 192) return launch_gemm<192, MV_GEMM_LINEAR>(a, stream);
-      if (use_pair && bn == 256) return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
+      if (use_pair && bn == 256) {
+        // fp32 residual-stream update (attn.proj / fc2 with LayerScale): TMA epilogue. MV_GEMM_EPI_TMA=0 keeps the old one.
+        static const int epi_env = [] { const char* e = getenv("MV_GEMM_EPI_TMA"); return e ? atoi(e) : 1; }();
+        if (epi_env != 0 && a.out_f32 == 1 && a.resid && !a.aux && a.act == MV_ACT_NONE && a.rows_per_group == 0 && a.n % 32 == 0 &&
+            a.ldo % 4 == 0 && a.ldr % 4 == 0)
+          return launch_gemm<256, MV_GEMM_LINEAR_TMA, true>(a, stream);
+        return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
+      }
       switch (bn) {
         case 16: return launch_gemm<16, MV_GEMM_LINEAR>(a, stream);
         case 32: return launch_gemm<32, MV_GEMM_LINEAR>(a, stream);

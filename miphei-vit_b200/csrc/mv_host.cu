@@ -140,6 +140,34 @@ const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t col
   return hand_out(tm);
 }
 
+const CUtensorMap* get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  TmapKey key{ptr, rows, cols, ld | (1ull << 62), box_rows, 32u};  // tag bit 62: fp32 map (never collides with bf16 keys)
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return hand_out(it->second);
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15)) {
+    set_error("fp32 TMA operand must be 16-byte aligned with a 16-byte multiple pitch (ptr %p ld %llu)", ptr, (unsigned long long)ld);
+    return nullptr;
+  }
+  void* mem = nullptr;
+  if (posix_memalign(&mem, 64, sizeof(CUtensorMap)) != 0) {
+    set_error("out of host memory");
+    return nullptr;
+  }
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(mem);
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * 4};
+  uint32_t box[2] = {32, box_rows};
+  if (encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) !=
+      MV_OK) {
+    free(mem);
+    return nullptr;
+  }
+  evict_if_full();
+  g_tmaps.emplace(key, tm);
+  return hand_out(tm);
+}
+
 const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, int c, int tw, int th, int stride) {
   // key reuse: rows = batch<<32|h, cols = w<<32|c, ld = stride, box = (th, tw) with a tag bit so 2-D maps never collide
   TmapKey key{ptr, ((uint64_t)batch << 32) | (uint32_t)h, ((uint64_t)w << 32) | (uint32_t)c, (uint64_t)stride | (1ull << 63),

@@ -24,6 +24,9 @@ bool first_use_on_device(std::atomic<uint64_t>& mask);
 // thread-local COPY valid until the calling thread's 16th following lookup (pass it to the kernel by value).
 const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                     uint32_t box_cols = 64);
+// 2-D fp32 row-major map with a 32-column (128-byte) x box_rows box, 128-byte swizzle: residual-stream tiles read / written
+// by the TMA epilogue of the fp32-residual GEMM. Cached like the bf16 maps.
+const CUtensorMap* get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 // 4-D NHWC bf16 map [B, H, W, C] with box {64 channels, tw*stride, th*stride, 1} traversed with element stride
 // `stride` in W and H (tw x th pixels land in smem as 128-byte rows, 128-byte swizzle). Cached.
 const CUtensorMap* get_tmap_nhwc_bf16(const void* ptr, int batch, int h, int w, int c, int tw, int th, int stride);

@@ -196,3 +196,32 @@ def test_gemm_stream_k_swiglu_fwd_bwd():
     g1 = ops.gemm(dx, w2t, mode=ops.GEMM_SWIGLU_BWD, in2=aux0, stream_k="force")
     assert (g1.float() - g0.float()).abs().max().item() <= 2e-2 * g0.float().abs().max().item()
     assert int(ops._sk_workspace(x.device).count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(5264, 1536, 1536), (5264, 1536, 4096), (10528, 1536, 1536), (1040, 512, 128), (2049, 768, 640)])
+def test_gemm_fp32_residual_tma_epilogue(M, N, K):
+    """attn.proj / fc2 form: x_out = (a @ w^T) * ls + ls*b + x, fp32 residual stream.  On CTA pairs the residual tiles come in
+    and the results go out as TMA bulk copies through swizzled shared memory (no per-thread global access); the single-CTA
+    kernel keeps the register epilogue — both must match the fp32 reference, out of place and in place, M tails included."""
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    w = _rand((N, K), 0.05, 2).bfloat16()
+    scale, shift, resid = _rand((N,), 0.3, 3), _rand((N,), 0.3, 4), _rand((M, N), 1.0, 5)
+    ref = (a.float() @ w.float().t()) * scale + shift + resid
+    old = ops.gemm(a, w, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, block_n=256, pair=1)
+    new = ops.gemm(a, w, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, block_n=256, pair=2)
+    _close(new, ref, 2e-5)
+    assert (new - old).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    x = resid.clone()                                   # in place: out aliases the residual (what the engine does)
+    for _ in range(2):
+        ops.gemm(a, w, scale=scale, shift=shift, resid=x, out=x, pair=2)
+    _close(x, ref + (ref - resid), 4e-5)
+    nos = ops.gemm(a, w, resid=resid, out_dtype=torch.float32, pair=2)   # no scale / shift
+    _close(nos, a.float() @ w.float().t() + resid, 2e-5)
+    big = torch.full((M + 64, N + 32), 7.0, device="cuda")               # strided output / residual views, guard band untouched
+    view = big[32:32 + M, 32:32 + N]
+    view.copy_(resid)
+    ops.gemm(a, w, scale=scale, shift=shift, resid=view, out=view, pair=2)
+    _close(view, ref, 2e-5)
+    assert float((big[:32] - 7).abs().max()) == 0 and float((big[32 + M:] - 7).abs().max()) == 0
+    assert float((big[:, :32] - 7).abs().max()) == 0
