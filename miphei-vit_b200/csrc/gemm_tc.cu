@@ -17,6 +17,9 @@ namespace mv {
 // internal mode (never passed through the C ABI): LINEAR with fp32 output + fp32 residual whose epilogue moves the residual in
 // and the result out with TMA (bulk async copies through swizzled shared-memory tiles) instead of per-thread ld / st
 constexpr int MV_GEMM_LINEAR_TMA = 16;
+// internal mode: LINEAR with bf16 output, no residual (QKV, the dX GEMMs): accumulator -> scale / shift (/ ReLU) -> bf16 ->
+// swizzled shared-memory tile -> one TMA store per 32 rows x 64 columns; no transpose staging, no per-thread global store
+constexpr int MV_GEMM_LINEAR_TMA_BF16 = 17;
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
@@ -143,10 +146,10 @@ struct GemmCfg {
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = gemm_epi_warps(MODE, BLOCK_N, LIGHT);
-  static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA;
+  static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA || MODE == MV_GEMM_LINEAR_TMA_BF16;
   // LINEAR_TMA: per epilogue warp kTmaResStages residual tiles + kTmaOutStages output tiles of 32 rows x 32 fp32 columns
   // (4 KB each, 128-byte swizzle, 1 KB aligned) directly behind the operand ring; the transpose staging is not needed there
-  static constexpr int kTmaResStages = 2, kTmaOutStages = 1;
+  static constexpr int kTmaResStages = MODE == MV_GEMM_LINEAR_TMA ? 2 : 0, kTmaOutStages = MODE == MV_GEMM_LINEAR_TMA ? 1 : 2;
   static constexpr int kEpiTmaBytes = kEpiTma ? kEpiWarps * (kTmaResStages + kTmaOutStages) * 4096 : 0;
   static constexpr int kStagingBytes = kEpiTma ? 0 : kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
@@ -583,7 +586,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       float* coef = coef_all + ew * (2 * BLOCK_N);
-      if constexpr ((MODE == MV_GEMM_LINEAR || MODE == MV_GEMM_LINEAR_TMA) && BLOCK_N >= 32) {
+      if constexpr ((MODE == MV_GEMM_LINEAR || Cfg::kEpiTma) && BLOCK_N >= 32) {
         // this tile's (scale, shift) columns -> warp-private smem, also ahead of the accumulator wait
 #pragma unroll
         for (int i = lane * 4; i < BLOCK_N; i += 128) {
@@ -929,6 +932,52 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_commit();
           }
         }
+      } else if constexpr (MODE == MV_GEMM_LINEAR_TMA_BF16) {
+        // out = act(acc * scale + shift) in bf16: 32 rows x 64 columns (128-byte rows) per step and warp, written row per lane
+        // into the 128-byte-swizzled tile a TMA store expects; output stages alternate so that a store drains while the next
+        // chunk is converted.
+        constexpr int NC = BLOCK_N / 64;
+        const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
+        const int swz = lane & 7;
+        const bool relu = p.act == MV_ACT_RELU;
+        uint32_t v0[32], v1[32];
+        acc_ld32(0, v0);
+        acc_ld32(32, v1);
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          acc_wait();
+          uint32_t pk[32];  // 64 bf16
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t* vv = h ? v1 : v0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sc = *reinterpret_cast<const float4*>(coef + c * 64 + h * 32 + 4 * j);
+              const float4 sh = *reinterpret_cast<const float4*>(coef + BLOCK_N + c * 64 + h * 32 + 4 * j);
+              float f0 = fmaf(__uint_as_float(vv[4 * j + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(vv[4 * j + 1]), sc.y, sh.y);
+              float f2 = fmaf(__uint_as_float(vv[4 * j + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(vv[4 * j + 3]), sc.w, sh.w);
+              if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+              pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
+              pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
+            }
+          }
+          if (c + 1 < NC) {
+            acc_ld32((c + 1) * 64, v0);
+            acc_ld32((c + 1) * 64 + 32, v1);
+          }
+          if (lane == 0) tma_store_wait_read<TO - 1>();  // the store that last used this output stage has drained it
+          __syncwarp();
+          uint8_t* os = tma_epi_gen + (c % TO) * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(os + ((j ^ swz) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_o, tma_epi_base + (c % TO) * 4096u, n_blk * BLOCK_N + c * 64, m_warp);
+            tma_store_commit();
+          }
+        }
       } else if constexpr (MODE == MV_GEMM_LINEAR) {
         constexpr int CH = 16;
 #pragma unroll 1
@@ -1178,7 +1227,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (MODE == MV_GEMM_LINEAR && p.colstats && stat_nblk >= 0) flush_stats(stat_nblk);
-    if constexpr (MODE == MV_GEMM_LINEAR_TMA) {
+    if constexpr (Cfg::kEpiTma) {
       if (lane == 0) tma_store_wait<0>();  // every output tile has landed before the CTA retires
     }
   }
@@ -1248,6 +1297,9 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
     tr = get_tmap_2d_f32(a.resid, a.m, a.n, a.ldr, 32);
     to = get_tmap_2d_f32(a.out, a.m, a.n, a.ldo, 32);
     if (!tr || !to) return MV_ERR_ARG;
+  } else if (MODE == MV_GEMM_LINEAR_TMA_BF16) {
+    to = get_tmap_2d_bf16(a.out, a.m, a.n, a.ldo, 32, 64);
+    if (!to) return MV_ERR_ARG;
   }
   const CUtensorMap* tb = tb_conv ? tb_conv
                           : MODE == MV_GEMM_NN_ATOMIC ? get_tmap_2d_bf16(a.b, a.k, a.n, a.ldb, 64)
@@ -1451,6 +1503,9 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
         if (epi_env != 0 && a.out_f32 == 1 && a.resid && !a.aux && a.act == MV_ACT_NONE && a.rows_per_group == 0 && a.n % 32 == 0 &&
             a.ldo % 4 == 0 && a.ldr % 4 == 0)
           return launch_gemm<256, MV_GEMM_LINEAR_TMA, true>(a, stream);
+        if (epi_env != 0 && epi_env != 2 && a.out_f32 == 0 && a.out && !a.resid && !a.aux && !a.colstats && a.rows_per_group == 0 &&
+            (a.act == MV_ACT_NONE || a.act == MV_ACT_RELU) && a.ldo % 8 == 0)
+          return launch_gemm<256, MV_GEMM_LINEAR_TMA_BF16, true>(a, stream);
         return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
       }
       switch (bn) {

@@ -225,3 +225,26 @@ def test_gemm_fp32_residual_tma_epilogue(M, N, K):
     _close(view, ref, 2e-5)
     assert float((big[:32] - 7).abs().max()) == 0 and float((big[32 + M:] - 7).abs().max()) == 0
     assert float((big[:, :32] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(5264, 4608, 1536), (10528, 1536, 1536), (1040, 512, 128), (2049, 776, 640)])
+def test_gemm_bf16_out_tma_epilogue(M, N, K):
+    """QKV / dX form on CTA pairs: act(acc * scale + shift) -> bf16 through swizzled shared memory and TMA stores; must agree
+    with the register epilogue of the single-CTA kernel bit for bit (same fp32 math, same rounding), tails and strides included"""
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    w = _rand((N, K), 0.05, 2).bfloat16()
+    scale, shift = _rand((N,), 0.5, 3), _rand((N,), 0.5, 4)
+    ref = (a.float() @ w.float().t()) * scale + shift
+    for act in (ops.ACT_NONE, ops.ACT_RELU):
+        r = torch.relu(ref) if act == ops.ACT_RELU else ref
+        old = ops.gemm(a, w, scale=scale, shift=shift, act=act, block_n=256, pair=1)
+        new = ops.gemm(a, w, scale=scale, shift=shift, act=act, block_n=256, pair=2)
+        _close(new, r, 1e-2)
+        assert torch.equal(old, new)
+    big = torch.full((M + 8, N + 16), 3.0, dtype=torch.bfloat16, device="cuda")   # strided output view, guard band untouched
+    view = big[8:, 8:8 + N]
+    ops.gemm(a, w, shift=shift, out=view, pair=2)
+    _close(view, a.float() @ w.float().t() + shift, 1e-2)
+    assert float((big[:8].float() - 3).abs().max()) == 0 and float((big[:, :8].float() - 3).abs().max()) == 0
+    assert float((big[:, 8 + N:].float() - 3).abs().max()) == 0
