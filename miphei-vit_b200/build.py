@@ -26,13 +26,17 @@ def _newest_header():
     return t
 
 
-def build(verbose=False, force=False, prof=False):
+def build(verbose=False, force=False, prof=False, variant=None, defines=()):
     """prof=True builds the diagnostic twin libmiphei_b200_prof.so (-DMV_GEMM_PROFILE=1: per-role cycle counters in the
     GEMM kernel, tools/gemm_roles.py); the production library carries no instrumentation."""
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     bdir = os.path.join(CSRC, "build_prof" if prof else "build")
     flags = FLAGS + (["-DMV_GEMM_PROFILE=1"] if prof else [])
     out = OUT.replace(".so", "_prof.so") if prof else OUT
+    if variant:  # experiment builds (A/B of compile-time constants): libmiphei_b200_<variant>.so, selected with MIPHEI_B200_LIB
+        bdir = os.path.join(CSRC, "build_" + variant)
+        flags = FLAGS + ["-D" + d for d in defines]
+        out = OUT.replace(".so", "_%s.so" % variant)
     os.makedirs(bdir, exist_ok=True)
     hdr_t = _newest_header()
     jobs = []
@@ -70,4 +74,7 @@ def build(verbose=False, force=False, prof=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, prof="--prof" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, prof="--prof" in sys.argv, variant=var[0] if var else None,
+                defines=defs))

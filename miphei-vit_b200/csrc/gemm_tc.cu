@@ -16,6 +16,15 @@ namespace mv {
 
 // internal mode (never passed through the C ABI): LINEAR with fp32 output + fp32 residual whose epilogue moves the residual in
 // and the result out with TMA (bulk async copies through swizzled shared-memory tiles) instead of per-thread ld / st
+#ifndef MV_TMA_RES_STAGES
+#define MV_TMA_RES_STAGES 2        // residual tiles in flight per epilogue warp (fp32-residual epilogue)
+#endif
+#ifndef MV_TMA_OUT_STAGES_F32
+#define MV_TMA_OUT_STAGES_F32 1    // output staging tiles per epilogue warp, fp32-residual epilogue (5 operand stages remain)
+#endif
+#ifndef MV_TMA_OUT_STAGES_BF16
+#define MV_TMA_OUT_STAGES_BF16 2   // output staging tiles per epilogue warp, bf16 epilogue (5 operand stages remain; 1 -> 6)
+#endif
 constexpr int MV_GEMM_LINEAR_TMA = 16;
 // internal mode: LINEAR with bf16 output, no residual (QKV, the dX GEMMs): accumulator -> scale / shift (/ ReLU) -> bf16 ->
 // swizzled shared-memory tile -> one TMA store per 32 rows x 64 columns; no transpose staging, no per-thread global store
@@ -149,7 +158,8 @@ struct GemmCfg {
   static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA || MODE == MV_GEMM_LINEAR_TMA_BF16;
   // LINEAR_TMA: per epilogue warp kTmaResStages residual tiles + kTmaOutStages output tiles of 32 rows x 32 fp32 columns
   // (4 KB each, 128-byte swizzle, 1 KB aligned) directly behind the operand ring; the transpose staging is not needed there
-  static constexpr int kTmaResStages = MODE == MV_GEMM_LINEAR_TMA ? 2 : 0, kTmaOutStages = MODE == MV_GEMM_LINEAR_TMA ? 1 : 2;
+  static constexpr int kTmaResStages = MODE == MV_GEMM_LINEAR_TMA ? MV_TMA_RES_STAGES : 0;
+  static constexpr int kTmaOutStages = MODE == MV_GEMM_LINEAR_TMA ? MV_TMA_OUT_STAGES_F32 : MV_TMA_OUT_STAGES_BF16;
   static constexpr int kEpiTmaBytes = kEpiTma ? kEpiWarps * (kTmaResStages + kTmaOutStages) * 4096 : 0;
   static constexpr int kStagingBytes = kEpiTma ? 0 : kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
