@@ -23,7 +23,7 @@ namespace mv {
 #define MV_TMA_OUT_STAGES_F32 1    // output staging tiles per epilogue warp, fp32-residual epilogue (5 operand stages remain)
 #endif
 #ifndef MV_TMA_OUT_STAGES_BF16
-#define MV_TMA_OUT_STAGES_BF16 2   // output staging tiles per epilogue warp, bf16 epilogue (5 operand stages remain; 1 -> 6)
+#define MV_TMA_OUT_STAGES_BF16 1   // output staging tiles per epilogue warp, bf16 epilogue (6 operand stages remain; 2 -> 5: measured equal)
 #endif
 constexpr int MV_GEMM_LINEAR_TMA = 16;
 // internal mode: LINEAR with bf16 output, no residual (QKV, the dX GEMMs): accumulator -> scale / shift (/ ReLU) -> bf16 ->
