@@ -108,7 +108,7 @@ struct SegIter {
     splits = p.splits;
     nkb = p.num_k_blocks;
     sk_dp = p.sk_dp;
-    dp_end = p.sk_rem > 0 ? p.sk_dp : num_mn * splits;
+    dp_end = p.sk_dp;  // = all tiles unless a stream-K remainder or a separately launched tail follows
     tile_next = unit;
     const long long wk = (long long)p.sk_rem * nkb;
     k_cur = wk * unit / units;
@@ -1264,8 +1264,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 static long long* g_gemm_prof = nullptr;  // diagnostics only (mv_gemm_set_profile_buffer)
 
 // ------------------------------------------------------------------ host launch
+// tile_limit > 0: only tiles [0, tile_limit) in m-fastest order are computed (the rest is launched separately, see
+// launch_with_tail)
 template <int BLOCK_N, int MODE, bool PAIR = false, bool LIGHT = false>
-static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
+static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream, int tile_limit = 0) {
   using Cfg = GemmCfg<BLOCK_N, MODE, PAIR, LIGHT>;
   static std::atomic<uint64_t> attr_set{0};  // one bit per device: function attributes are per device
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, MODE, PAIR, LIGHT>;
@@ -1349,7 +1351,8 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.conv_cb0 = (a.conv_c0 + 63) / 64;
   p.conv_cb1 = (a.conv_c1 + 63) / 64;
 
-  const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+  int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+  if (tile_limit > 0 && tile_limit < tiles) tiles = tile_limit;
   const int sms = device_sms() > 0 ? device_sms() : 148;
   int grid = sms;
   if (PAIR) grid &= ~1;
@@ -1361,7 +1364,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   p.sk_ws = nullptr;
   p.sk_cnt = nullptr;
   static const int sk_env = [] { const char* e = getenv("MV_GEMM_SK"); return e ? atoi(e) : 1; }();  // 0 off, 1 auto, 2 always
-  if (gemm_sk_mode(MODE, BLOCK_N) && !LIGHT && sk_env != 0 && a.reserved3 != 2 && a.workspace && !a.conv && !a.colstats && a.rows_per_group == 0 &&
+  if (gemm_sk_mode(MODE, BLOCK_N) && !LIGHT && sk_env != 0 && a.reserved3 != 2 && a.workspace && tile_limit <= 0 && !a.conv && !a.colstats && a.rows_per_group == 0 &&
       a.kskip_end == 0 && p.splits == 1 && (reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0) {
     const int rem = tiles % units_full;
     const long long wk = (long long)rem * p.num_k_blocks;
@@ -1385,6 +1388,42 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream) {
   MV_LAUNCH(kern, grid, gemm_threads(MODE, BLOCK_N, LIGHT), Cfg::kSmemBytes, stream, *ta, *ta2, *tb, *tr, *to, p);
   MV_CHECK_LAUNCH("gemm_bf16_tc");
   return MV_OK;
+}
+
+// Tail re-tiling for the CTA-pair LINEAR GEMMs: T tiles of 256 x 256 on U = SMs / 2 pairs leave a last wave of R = T mod U
+// tiles in which U - R pairs idle for a whole tile time. When those R tiles form one rectangle (they do whenever R <= the
+// number of 256-row blocks: tiles are ordered m-fastest, so they are the bottom rows of the last 256-column block), the main
+// launch stops after the full waves and the rectangle is computed by a second launch of 128 x 128 single-CTA tiles, which
+// spreads it over up to 148 SMs at a quarter of the work each — no reduction, no extra traffic (stream-K, which needs one, was
+// measured slower: DESIGN.md 3.1). Returns the number of leading tiles the main launch keeps (0 = no split) and fills `tail`.
+static int plan_tail(const mv_gemm_args& a, mv_gemm_args* tail) {
+  static const int tail_env = [] { const char* e = getenv("MV_GEMM_TAIL"); return e ? atoi(e) : 1; }();
+  if (tail_env == 0 || a.aux || a.colstats || a.rows_per_group || a.kskip_end || a.conv || a.act == MV_ACT_GATE_MASK) return 0;
+  const int sms = device_sms() > 0 ? device_sms() : 148;
+  const int units = (sms & ~1) / 2;
+  const int mp = (a.m + 255) / 256, nb = (a.n + 255) / 256;
+  const int tiles = mp * nb, full = tiles / units, rem = tiles % units;
+  if (full < 1 || rem == 0 || rem > mp) return 0;
+  const int row0 = (mp - rem) * 256, col0 = (nb - 1) * 256;
+  const int rows = a.m - row0, cols = a.n - col0;
+  const int tail_tiles = ((rows + 127) / 128) * ((cols + 127) / 128);
+  // cost of the tail in pair-tile times: quarter-size tiles, ~1.3x less efficient, in waves of `sms` tiles
+  const double tail_cost = 0.5 * 1.3 * ((tail_tiles + sms - 1) / sms);
+  if (tail_cost > 0.85) return 0;
+  *tail = a;
+  const size_t osz = a.out_f32 == 1 ? 4 : 2;
+  tail->a = reinterpret_cast<const uint8_t*>(a.a) + (size_t)row0 * a.lda * 2;
+  tail->b = reinterpret_cast<const uint8_t*>(a.b) + (size_t)col0 * a.ldb * 2;
+  tail->m = rows;
+  tail->n = cols;
+  tail->out = reinterpret_cast<uint8_t*>(a.out) + ((size_t)row0 * a.ldo + col0) * osz;
+  if (a.resid) tail->resid = a.resid + (size_t)row0 * a.ldr + col0;
+  if (a.scale) tail->scale = a.scale + col0;
+  if (a.shift) tail->shift = a.shift + col0;
+  tail->block_n = 128;
+  tail->reserved2 = 1;  // single CTAs
+  tail->workspace = nullptr;
+  return tiles - rem;
 }
 
 }  // namespace mv
@@ -1510,13 +1549,19 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
       if (use_pair && bn == 256) {
         // fp32 residual-stream update (attn.proj / fc2 with LayerScale): TMA epilogue. MV_GEMM_EPI_TMA=0 keeps the old one.
         static const int epi_env = [] { const char* e = getenv("MV_GEMM_EPI_TMA"); return e ? atoi(e) : 1; }();
+        mv_gemm_args tail;
+        const int keep = a.block_n == 0 ? plan_tail(a, &tail) : 0;  // (an explicit block_n pins the single-launch schedule)
+        int rc;
         if (epi_env != 0 && a.out_f32 == 1 && a.resid && !a.aux && a.act == MV_ACT_NONE && a.rows_per_group == 0 && a.n % 32 == 0 &&
             a.ldo % 4 == 0 && a.ldr % 4 == 0)
-          return launch_gemm<256, MV_GEMM_LINEAR_TMA, true>(a, stream);
-        if (epi_env != 0 && epi_env != 2 && a.out_f32 == 0 && a.out && !a.resid && !a.aux && !a.colstats && a.rows_per_group == 0 &&
-            (a.act == MV_ACT_NONE || a.act == MV_ACT_RELU) && a.ldo % 8 == 0)
-          return launch_gemm<256, MV_GEMM_LINEAR_TMA_BF16, true>(a, stream);
-        return launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream);
+          rc = launch_gemm<256, MV_GEMM_LINEAR_TMA, true>(a, stream, keep);
+        else if (epi_env != 0 && epi_env != 2 && a.out_f32 == 0 && a.out && !a.resid && !a.aux && !a.colstats &&
+                 a.rows_per_group == 0 && (a.act == MV_ACT_NONE || a.act == MV_ACT_RELU) && a.ldo % 8 == 0)
+          rc = launch_gemm<256, MV_GEMM_LINEAR_TMA_BF16, true>(a, stream, keep);
+        else
+          rc = launch_gemm<256, MV_GEMM_LINEAR, true>(a, stream, keep);
+        if (rc != MV_OK || keep == 0) return rc;
+        return mv_gemm_bf16(&tail, stream_);  // the last partial wave as 128 x 128 single-CTA tiles
       }
       switch (bn) {
         case 16: return launch_gemm<16, MV_GEMM_LINEAR>(a, stream);

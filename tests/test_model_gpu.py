@@ -53,11 +53,19 @@ def test_infer_matches_reference_golden(name):
     with torch.no_grad():
         again = model(x.cuda())
     assert torch.equal(again, got)
-    # uint8 sink (src/callbacks.py:345-346): +-1 LSB of the truncated reference mapping, a few more where bf16 error
-    # crosses an integer boundary
+    # uint8 sink (src/callbacks.py:345-346): u8 = trunc(clamp((p + 0.9) / 1.8, 0, 1) * 255), i.e. 141.7 LSB per unit of p.
+    # (1) the fused sink is the truncated mapping of the kernel's OWN fp32 output (at most 1 LSB where the two evaluations of
+    #     (p + 0.9) / 1.8 * 255 straddle an integer);
+    # (2) against the reference golden the bound follows from the measured prediction error: ceil(141.7 * max|p - p_ref|) + 1
+    #     LSB (truncation can add one), and it must stay within 4 LSB (max-rel-err 0.025 x max|p| of these models ~ 3 LSB).
     u8 = model.engine.infer(x.cuda(), out_dtype=torch.uint8).cpu()
+    own8 = (((got.float().cpu() + 0.9) / 1.8).clamp(0, 1) * 255).to(torch.uint8)
+    assert (u8.int() - own8.int()).abs().max().item() <= 1
     ref8 = (((g["pred_eval"] + 0.9) / 1.8).clamp(0, 1) * 255).to(torch.uint8)
-    assert (u8.int() - ref8.int()).abs().max().item() <= 8
+    err = (got.float().cpu() - g["pred_eval"]).abs().max().item()
+    bound = int(-(-141.7 * err // 1)) + 1
+    worst = (u8.int() - ref8.int()).abs().max().item()
+    assert worst <= bound and worst <= 4, (worst, bound, err)
     assert (u8.int() - ref8.int()).abs().float().mean().item() < 0.6
 
 
