@@ -117,7 +117,9 @@ typedef struct mv_gemm_args {
                          The training-mode decoder keeps feature maps and conv weights in fp16: the
                          reference trains under fp16 autocast (configs/config.yaml:23) and the LoRA gradients need the
                          extra mantissa bits. Outputs are unaffected. */
-  int32_t reserved3;  /* stream-K policy: 0 = when worthwhile, 1 = whenever legal, 2 = never */
+  int32_t reserved3;  /* schedule experiments for the last, partial wave of tiles (both measured slower than leaving it partly
+                         idle): 0 = stream-K when the library judges it worthwhile (needs `workspace`),
+                         1 = stream-K whenever legal, 2 = never, 3 = re-tile the last wave as 128 x 128 tiles in a 2nd launch */
   void* workspace;    /* optional, 256-byte aligned, ZERO-INITIALISED ONCE by the caller and then left to the library (it
                          restores the zeros): lets LINEAR / SWIGLU / SWIGLU_BWD GEMMs spread the k blocks of their last,
                          partial wave of tiles over all SMs (stream-K; partial sums meet here). One workspace per stream:

@@ -1395,10 +1395,13 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream, int tile_limi
 // number of 256-row blocks: tiles are ordered m-fastest, so they are the bottom rows of the last 256-column block), the main
 // launch stops after the full waves and the rectangle is computed by a second launch of 128 x 128 single-CTA tiles, which
 // spreads it over up to 148 SMs at a quarter of the work each — no reduction, no extra traffic (stream-K, which needs one, was
-// measured slower: DESIGN.md 3.1). Returns the number of leading tiles the main launch keeps (0 = no split) and fills `tail`.
+// measured slower: DESIGN.md 3.1). NEGATIVE RESULT as well, kept behind a switch (see below). Returns the number of leading tiles the main launch keeps (0 = no split) and fills `tail`.
 static int plan_tail(const mv_gemm_args& a, mv_gemm_args* tail) {
-  static const int tail_env = [] { const char* e = getenv("MV_GEMM_TAIL"); return e ? atoi(e) : 1; }();
-  if (tail_env == 0 || a.aux || a.colstats || a.rows_per_group || a.kskip_end || a.conv || a.act == MV_ACT_GATE_MASK) return 0;
+  // measured SLOWER than leaving the last wave partly idle (QKV 60.6 -> 71.8 us at M = 5264: the tail launch pays its own
+  // prologue, runs the register epilogue on few SMs and cannot overlap the main launch, whose CTAs all end together), so it is
+  // off unless asked for: MV_GEMM_TAIL=1 or reserved3 == 3
+  static const int tail_env = [] { const char* e = getenv("MV_GEMM_TAIL"); return e ? atoi(e) : 0; }();
+  if ((tail_env == 0 && a.reserved3 != 3) || a.aux || a.colstats || a.rows_per_group || a.kskip_end || a.conv || a.act == MV_ACT_GATE_MASK) return 0;
   const int sms = device_sms() > 0 ? device_sms() : 148;
   const int units = (sms & ~1) / 2;
   const int mp = (a.m + 255) / 256, nb = (a.n + 255) / 256;

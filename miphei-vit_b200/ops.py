@@ -56,7 +56,7 @@ def _sk_workspace(device):
 def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows=None, scale=None, shift=None,
          resid=None, act=ACT_NONE, aux=None, in2=None, rows_per_group=0, group_stride=0, row_offset=0,
          resid_row_mod=False, block_n=0, conv=None, out_kind=None, colstats=None, no_out=False, pair=0,
-         kskip=None, stream_k=False):
+         kskip=None, stream_k=False, tail=False):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 GEMM (mv_gemm_bf16). See include/miphei_b200.h.
     stream_k: False (default) | True (when the library judges it worthwhile) | "force" — measured slower on every encoder
     shape (the L2 reduction of the partial tiles costs more than the idle last wave), kept for small grids."""
@@ -159,6 +159,8 @@ def gemm(a, b, *, mode=GEMM_LINEAR, out=None, out_dtype=torch.bfloat16, out_rows
         if ws is not None:
             args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
             args.reserved3 = 1 if stream_k == "force" else 0
+    if tail:
+        args.reserved3 = 3
     if kskip is not None:  # K range with all-zero B columns: never loaded
         args.kskip_begin, args.kskip_end = int(kskip[0]), int(kskip[1])
     _lib.check(lib.mv_gemm_bf16(ctypes.byref(args), _stream()), "mv_gemm_bf16")

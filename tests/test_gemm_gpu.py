@@ -252,21 +252,21 @@ def test_gemm_bf16_out_tma_epilogue(M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(10528, 1536, 1536), (10528, 1536, 4096), (5264, 4608, 1536), (4000, 768, 256)])
 def test_gemm_tail_retiling(M, N, K):
-    """default schedule of the big CTA-pair GEMMs: full waves of 256 x 256 tiles, then the partial last wave re-launched as
-    128 x 128 single-CTA tiles over its rectangle (no reduction). Same results as the single-CTA kernel, fp32-residual and
-    bf16 forms, in place too."""
+    """optional schedule of the big CTA-pair GEMMs (measured slower, off by default): full waves of 256 x 256 tiles, then the
+    partial last wave re-launched as 128 x 128 single-CTA tiles over its rectangle (no reduction). Same results as the
+    single-CTA kernel, fp32-residual and bf16 forms, in place too."""
     ops = _ops()
     a = _rand((M, K), 1.0, 1).bfloat16()
     w = _rand((N, K), 0.05, 2).bfloat16()
     scale, shift, resid = _rand((N,), 0.3, 3), _rand((N,), 0.3, 4), _rand((M, N), 1.0, 5)
     ref = (a.float() @ w.float().t()) * scale + shift + resid
     old = ops.gemm(a, w, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, block_n=256, pair=1)
-    new = ops.gemm(a, w, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32)
+    new = ops.gemm(a, w, scale=scale, shift=shift, resid=resid, out_dtype=torch.float32, tail=True)
     _close(new, ref, 2e-5)
     assert (new - old).abs().max().item() <= 2e-6 * ref.abs().max().item()
     x = resid.clone()
-    ops.gemm(a, w, scale=scale, shift=shift, resid=x, out=x)
+    ops.gemm(a, w, scale=scale, shift=shift, resid=x, out=x, tail=True)
     assert torch.equal(x, new)
     oldb = ops.gemm(a, w, scale=scale, shift=shift, act=ops.ACT_RELU, block_n=256, pair=1)
-    newb = ops.gemm(a, w, scale=scale, shift=shift, act=ops.ACT_RELU)
+    newb = ops.gemm(a, w, scale=scale, shift=shift, act=ops.ACT_RELU, tail=True)
     assert torch.equal(oldb, newb)
