@@ -18,7 +18,7 @@ python tools/ncu_summary.py $O/r02_train_full.ncu-rep $O/r02_ncu_full_train_b32.
 python tools/ncu_summary.py $O/r02_train_gemm_full.ncu-rep $O/r02_ncu_full_train_gemms_b32.csv > /dev/null 2>&1
 rm -f $O/*.ncu-rep   # the reports exceed what gpurun copies back; the per-kernel CSV summaries above are what is kept
 python tools/summarize_launches.py $O/r02_launches_infer_d4.csv > $O/r02_launches_infer_d4.txt 2>&1
-python tools/summarize_launches.py $O/r02_launches_train_d4.csv > $O/r02_launches_train_d4.txt 2>&1
+python tools/summarize_launches.py $O/r02_launches_train_d4.csv lora_refresh > $O/r02_launches_train_d4.txt 2>&1
 python tools/summarize_launches.py $O/r02_launches_bench.csv > $O/r02_launches_bench.txt 2>&1
 timeout 600 python tools/time_ops.py infer 16 > $O/r02_ops_infer.txt 2>&1
 timeout 600 python tools/time_ops.py train 32 > $O/r02_ops_train.txt 2>&1
