@@ -11,7 +11,7 @@ Configs (BASELINE.json `configs`).  A "step" is one pass of the hot p
   c3            training step (fwd + bwd + weighted MSE + clip + Adam), batch 32 per GPU, NCCL gradient all-reduce.
                 `value`: x, y resident; `e2e`: x, y in pinned host memory, H2D every step, loss read back.
   c4            HEMIT-style 3-channel head on 512-px tiles (1301 tokens), training, batch 8 per GPU.
-  c5            whole-slide sweep: 4096 raw uint8 tiles in host memory, batch 64, sharded round-robin over the ranks through
+  c5            whole-slide sweep: 16384 raw uint8 tiles in host memory, batch 64, sharded round-robin over the ranks through
                 wsi.infer_slide (loader workers -> pinned ring -> infer_stream -> uint8 predictions on the host); strong scaling.
 Every number is measured on the device with CUDA events, after >= 3 warm-up steps, max over ranks.
 """
@@ -243,7 +243,7 @@ def workload_name(c):
             "c3": "ORION training step (BASELINE configs[2]): fwd + bwd + weighted MSE + clip + Adam, batch 32 per GPU, "
                   "256-px tiles, 16 channels, NCCL gradient all-reduce",
             "c4": "HEMIT-style 3-channel head on 512-px tiles (BASELINE configs[3]): training step, batch 8 per GPU, 1301 tokens",
-            "c5": "whole-slide tiled inference sweep (BASELINE configs[4]): 4096 raw uint8 256-px tiles from host memory, "
+            "c5": "whole-slide tiled inference sweep (BASELINE configs[4]): raw uint8 256-px tiles of one slide from host memory, "
                   "batch 64, sharded round-robin over the GPUs"}[c]
 
 
@@ -593,7 +593,8 @@ def run_c5(cx):
     cx.barrier()
     t0 = time.perf_counter()
     e0.record()
-    n = wsi.infer_slide(model, tiles, batch=B, rank=rank, world=world, num_workers=args.workers)
+    st = {}
+    n = wsi.infer_slide(model, tiles, batch=B, rank=rank, world=world, num_workers=args.workers, stats=st)
     e1.record()
     cx.barrier()
     wall = time.perf_counter() - t0
@@ -611,7 +612,11 @@ def run_c5(cx):
         line["config"].update({"tiles": n_tiles, "batch": B, "loader_workers_per_gpu": args.workers,
                                "parallelism": "tiles sharded round-robin x%d, no collective" % world, "gf_per_tile": GF[256]["fwd"]})
         line["value_note"] = "forward at batch %d with inputs resident in HBM (per-GPU x N)" % B
+        steady = (st["tiles"] - 2 * B) / max(st["t_total_s"] - st["t_first_s"], 1e-9) * world if st.get("t_first_s") else None
         line["e2e"] = {"value": n_tiles / ms * 1e3, "unit": UNIT, "ms_total": ms, "wall_s": wall,
+                       "startup_s": st.get("t_first_s"), "steady_state_value": steady,
+                       "note": "value = all tiles / whole sweep INCLUDING loader-worker start-up (process forks) up to the first "
+                               "result (startup_s, rank 0); steady_state_value excludes it",
                        "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 16 * S * S),
                        "api": "wsi.infer_slide(model, tiles): %d loader worker processes -> shared pinned ring -> "
                               "engine.infer_stream (uint8 tiles normalised on the device, uint8 sink) -> host; the whole "
@@ -630,7 +635,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--train-batch", type=int, default=32)
-    ap.add_argument("--tiles", type=int, default=4096)
+    ap.add_argument("--tiles", type=int, default=16384, help="c5: tiles of the synthetic slide (a 20x slide has 10^4 - 10^5)")
     ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")

@@ -311,8 +311,10 @@ int mv_heads_bwd_stencil(const void* t, const void* ds, const void* gate, void* 
  *                       counts [batch, cap], n_unique [batch]; rows >= n_unique[b] are untouched. cap = power of two
  *                       >= the number of nuclei of any image; *overflow is set to 1 if an image has more (the caller
  *                       must pre-zero it and re-run with a larger cap).  target / means_target may both be NULL.
- *                       The tables live in shared memory while cap * (2 chans + 10) * 4 bytes fit in 220 KB; beyond that
- *                       (thousands of nuclei in one tile) pass a global workspace of mv_cell_means_workspace_bytes().
+ *                       workspace (256-byte aligned, mv_cell_means_workspace_bytes() bytes, contents irrelevant): while the
+ *                       tables fit in shared memory (cap * (2 chans + 10) * 4 bytes <= 220 KB) it holds the partial sums that
+ *                       let SEVERAL CTAs share one image (optional: NULL = one CTA per image); beyond that (thousands of
+ *                       nuclei in one tile) it holds the tables themselves and is required.
  *   mv_cell_means_bwd   the extractor is differentiable in the reference (training_step's cell loss, src/models.py:
  *                       120-131): d map[b, c, p] = d means[row(b, label p), c] / count[row], 0 on background; ids / counts /
  *                       n_unique are the packed forward outputs.

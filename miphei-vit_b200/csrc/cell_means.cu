@@ -25,20 +25,26 @@ __global__ void __launch_bounds__(CM_THREADS) cell_means_kernel(const float* __r
                                                                 float* __restrict__ means_pred, float* __restrict__ means_target,
                                                                 long long* __restrict__ ids, float* __restrict__ counts,
                                                                 int* __restrict__ n_unique, int* __restrict__ overflow,
-                                                                uint8_t* __restrict__ gws, long long gws_stride) {
+                                                                uint8_t* __restrict__ gws, long long gws_stride,
+                                                                float* __restrict__ gsum, int* __restrict__ gcnt) {
   griddep_sync();
   extern __shared__ __align__(16) uint8_t cm_smem[];
   const int hslots = 2 * cap;  // power of two
   // tables and accumulators: shared memory when they fit (the fast path), else this image's slice of a caller-provided
   // global workspace (images with thousands of nuclei: same algorithm, the atomics go to L2)
-  uint8_t* base = gws ? gws + (long long)blockIdx.x * gws_stride : cm_smem;
+  uint8_t* base = gws ? gws + (long long)blockIdx.y * gws_stride : cm_smem;
   long long* keys = reinterpret_cast<long long*>(base);                 // [hslots] 0 = empty
   long long* skey = keys + hslots;                                      // [cap] sort keys
   int* dense = reinterpret_cast<int*>(skey + cap);                      // [hslots] slot -> rank
   int* sslot = dense + hslots;                                          // [cap] sort payload (hash slot)
   float* acc = reinterpret_cast<float*>(sslot + cap);                   // [cap][2C + 1]
-  __shared__ int s_count, s_over;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_count, s_over, s_last;
+  // grid = (slices, images): every CTA of an image builds the same label table (labels are read by all of them — 1/17 of the
+  // traffic at 16 channels), then reduces only its slice of the pixels; partial sums meet in gsum, the last CTA finishes
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int slices = gridDim.x;
+  const int per_slice = ((HW + slices - 1) / slices + 31) & ~31;
+  const int p_lo = blockIdx.x * per_slice, p_hi = min(HW, p_lo + per_slice);
   const int W = 2 * C + 1;
   const LabelT* lab = nuclei + (long long)b * HW;
   const float* pb = pred + (long long)b * C * HW;
@@ -113,10 +119,10 @@ __global__ void __launch_bounds__(CM_THREADS) cell_means_kernel(const float* __r
   __syncthreads();
   // ---- pass B: accumulate (loop trip count is warp-uniform: __match_any_sync needs every lane)
   const int lane = tid & 31;
-  for (int p0 = (tid & ~31); p0 < HW; p0 += CM_THREADS) {
+  for (int p0 = p_lo + (tid & ~31); p0 < p_hi; p0 += CM_THREADS) {
     const int p = p0 + lane;
     int r = -1;
-    if (p < HW) {
+    if (p < p_hi) {
       const long long k = (long long)lab[p];
       if (k > 0) {
         int slot = hash(k);
@@ -171,6 +177,22 @@ __global__ void __launch_bounds__(CM_THREADS) cell_means_kernel(const float* __r
     }
   }
   __syncthreads();
+  if (slices > 1) {
+    // partial sums of this slice -> global; the CTA whose counter increment is the last one reads the totals back
+    float* gs = gsum + (long long)b * cap * W;
+    for (int i = tid; i < U * W; i += CM_THREADS) {
+      const float v = acc[i];
+      if (v != 0.f) atomicAdd(gs + i, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(gcnt + b, 1) == slices - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = tid; i < U * W; i += CM_THREADS) acc[i] = __ldcg(gs + i);
+    __syncthreads();
+  }
   // ---- means of this image (rows 0..U-1, ascending label)
   for (int i = tid; i < U * C; i += CM_THREADS) {
     const int r = i / C, c = i - r * C;
@@ -210,6 +232,12 @@ static size_t cm_smem_bytes(int C, int cap) {
   return (size_t)(2 * cap) * 8 + (size_t)cap * 8 + (size_t)(2 * cap) * 4 + (size_t)cap * 4 + (size_t)cap * (2 * C + 1) * 4;
 }
 constexpr size_t CM_SMEM_MAX = 220 * 1024;
+static int cm_slices(int batch) {
+  const int sms = device_sms() > 0 ? device_sms() : 148;
+  int s = (2 * sms + batch - 1) / batch;
+  return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+static size_t cm_gsum_bytes(int batch, int C, int cap) { return ((size_t)batch * cap * (2 * C + 1) * 4 + 255) / 256 * 256; }
 
 // Backward of the per-nucleus means: d pred[b, c, p] = d means[row(b, label p), c] / count[row] for labelled pixels, 0 on
 // background. ids / counts / n_unique are the forward's packed outputs (ids ascending per image): one binary search per pixel.
@@ -252,28 +280,44 @@ extern "C" int mv_cell_means(const float* pred, const float* target, const void*
   MV_CHECK_ARG((target == nullptr) == (means_target == nullptr), "mv_cell_means: target and means_target go together");
   size_t smem = cm_smem_bytes(chans, cap);
   const long long stride = (long long)((smem + 255) / 256 * 256);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   uint8_t* gws = nullptr;
-  if (smem > CM_SMEM_MAX) {  // tables in global memory
-    MV_CHECK_ARG(workspace && workspace_bytes >= stride * batch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+  float* gsum = nullptr;
+  int* gcnt = nullptr;
+  int slices = 1;
+  const long long need = mv_cell_means_workspace_bytes(batch, chans, cap);
+  if (smem > CM_SMEM_MAX) {  // tables in global memory (one CTA per image)
+    MV_CHECK_ARG(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                  "mv_cell_means: cap %d x %d channels exceeds shared memory: pass a 256-byte aligned workspace of "
-                 "mv_cell_means_workspace_bytes() = %lld bytes", cap, chans, stride * batch);
+                 "mv_cell_means_workspace_bytes() = %lld bytes", cap, chans, need);
     gws = reinterpret_cast<uint8_t*>(workspace);
     smem = 0;
+  } else if (workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0) {
+    // several CTAs per image: enough of them to cover the machine about twice
+    slices = cm_slices(batch);
+    if (slices > 1) {
+      gsum = reinterpret_cast<float*>(workspace);
+      gcnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + cm_gsum_bytes(batch, chans, cap));
+      cudaError_t em = cudaMemsetAsync(workspace, 0, (size_t)need, stream);
+      if (em != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(em));
+        return (int)em;
+      }
+    }
   }
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   cudaError_t e = cudaSuccess;
   if (label_bytes == 4) {
     e = cudaFuncSetAttribute(cell_means_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      MV_LAUNCH(cell_means_kernel<int32_t>, batch, CM_THREADS, smem, stream, pred, target, reinterpret_cast<const int32_t*>(nuclei),
-                chans, hw, cap, means_pred, means_target, reinterpret_cast<long long*>(ids), counts, n_unique, overflow, gws,
-                stride);
+      MV_LAUNCH(cell_means_kernel<int32_t>, dim3(slices, batch), CM_THREADS, smem, stream, pred, target,
+                reinterpret_cast<const int32_t*>(nuclei), chans, hw, cap, means_pred, means_target, reinterpret_cast<long long*>(ids),
+                counts, n_unique, overflow, gws, stride, gsum, gcnt);
   } else {
     e = cudaFuncSetAttribute(cell_means_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      MV_LAUNCH(cell_means_kernel<long long>, batch, CM_THREADS, smem, stream, pred, target,
+      MV_LAUNCH(cell_means_kernel<long long>, dim3(slices, batch), CM_THREADS, smem, stream, pred, target,
                 reinterpret_cast<const long long*>(nuclei), chans, hw, cap, means_pred, means_target,
-                reinterpret_cast<long long*>(ids), counts, n_unique, overflow, gws, stride);
+                reinterpret_cast<long long*>(ids), counts, n_unique, overflow, gws, stride, gsum, gcnt);
   }
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(cell_means): %s", cudaGetErrorString(e));
@@ -296,10 +340,12 @@ extern "C" int mv_cell_means_pack(const float* means_pred, const float* means_ta
   return MV_OK;
 }
 
-// bytes of global workspace mv_cell_means needs for this (batch, chans, cap); 0 when the tables fit in shared memory
+// bytes of global workspace mv_cell_means wants for this (batch, chans, cap): partial sums for several CTAs per image while
+// the tables fit in shared memory (optional: without it one CTA per image runs), the tables themselves beyond that (required)
 extern "C" int64_t mv_cell_means_workspace_bytes(int batch, int chans, int cap) {
   const size_t smem = mv::cm_smem_bytes(chans, cap);
-  if (smem <= mv::CM_SMEM_MAX) return 0;
+  if (smem <= mv::CM_SMEM_MAX)  // shared-memory tables: workspace = cross-CTA partial sums + per-image counters
+    return mv::cm_slices(batch) > 1 ? (int64_t)(mv::cm_gsum_bytes(batch, chans, cap) + ((size_t)batch * 4 + 255) / 256 * 256) : 0;
   return (int64_t)((smem + 255) / 256 * 256) * batch;
 }
 

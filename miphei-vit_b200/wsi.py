@@ -214,19 +214,25 @@ class TileStitcher:
 
 # ------------------------------------------------------------------------------------------------ the sweep
 def infer_slide(model, tiles, positions=None, batch=64, stitcher=None, rank=0, world=1, num_workers=0, prefetch_factor=2,
-                n_slots=None, on_batch=None):
+                n_slots=None, on_batch=None, stats=None):
     """Run the generator over the tiles of one slide (BASELINE configs[4]): `tiles` is any indexable of raw uint8 [S, S, 3]
     tiles (a Dataset reading regions of a slide in the reference); this rank takes tiles rank, rank + world, ...; loader
     workers fill a PinnedTileRing, engine.infer_stream normalises on the device and returns uint8 predictions, which go to
     `stitcher` (positions[i] = canvas (x, y) of tile i) and / or `on_batch(pred_u8_host, tile_indices)`.
-    Returns the number of tiles processed by this rank."""
+    Returns the number of tiles processed by this rank; `stats` (a dict) receives the time to the first result and the total.
+    The pinned ring is created once per (engine, batch, slots) and reused by later sweeps (page-locking ~150 MB is slow)."""
+    import time
+    t_start = time.perf_counter()
     eng = model.engine
     eng._ensure_packed()
     ids = list(shard_tiles(len(tiles), rank, world))
     depth = 2
     nw = int(num_workers)
     slots = n_slots if n_slots is not None else max(nw, 1) * max(prefetch_factor, 1) + depth + 2
-    ring = PinnedTileRing(slots, batch, eng.S)
+    rings = eng.__dict__.setdefault("_tile_rings", {})
+    ring = rings.get((slots, batch))
+    if ring is None:
+        ring = rings[(slots, batch)] = PinnedTileRing(slots, batch, eng.S)
     ds = RingBatchDataset(tiles, ring, ids)
     kw = dict(batch_size=None, shuffle=False, num_workers=nw)
     if nw > 0:
@@ -247,11 +253,15 @@ def infer_slide(model, tiles, positions=None, batch=64, stitcher=None, rank=0, w
 
     stream = eng.infer_stream(batches(), out_dtype=torch.uint8, depth=depth, device_sink=sink if stitcher is not None else None,
                               to_host=on_batch is not None or stitcher is None)
+    t_first = None
     for j, pred in enumerate(stream):
+        if t_first is None:
+            t_first = time.perf_counter() - t_start
         k, n = meta[j]
         if on_batch is not None:
             on_batch(pred[:n], ids[k * batch:k * batch + n])
         done += n
     torch.cuda.synchronize(eng.device)
-    ring.close()
+    if stats is not None:
+        stats.update(t_first_s=t_first, t_total_s=time.perf_counter() - t_start, tiles=done, batches=len(meta))
     return done
