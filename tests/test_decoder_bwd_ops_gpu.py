@@ -132,6 +132,24 @@ def test_transpose_with_ones_row():
     assert t.shape[0] == 40 and torch.equal(t[:32, :1000], x.t()) and (t[32, :1000] == 1).all() and (t[33:] == 0).all()
 
 
+@pytest.mark.parametrize("M,C", [(1000, 32), (4099, 48), (2048, 64), (777, 256), (65536, 32), (300, 8), (512, 30)])
+def test_transpose_shapes_formats_and_strides(M, C):
+    """register-transpose fast path (C % 8 == 0, aligned) and the generic kernel: row tails, strided input rows, fp16 input
+    converted to bf16 on the way, the row of ones"""
+    ops, _ = _mods()
+    x = _rand((M, C), 1.0, 1)
+    for dt in (torch.bfloat16, torch.float16):
+        xb = x.to(dt)
+        t = ops.transpose_bf16(xb)
+        assert t.dtype == torch.bfloat16 and torch.equal(t[:C, :M], xb.to(torch.bfloat16).t())
+        wide = _rand((M, C + 16), 1.0, 2).to(dt)          # strided rows (a channel slice of a wider map)
+        t2 = ops.transpose_bf16(wide[:, 8:8 + C])
+        assert torch.equal(t2[:C, :M], wide[:, 8:8 + C].to(torch.bfloat16).t())
+        if C % 8 == 0:
+            t3 = ops.transpose_bf16(xb, ones_row=True)
+            assert torch.equal(t3[:C, :M], xb.to(torch.bfloat16).t()) and bool((t3[C, :M] == 1).all()) and bool((t3[C + 1:] == 0).all())
+
+
 def test_gate_mask_epilogue():
     ops, _ = _mods()
     M, C, heads = 700, 32, 16
