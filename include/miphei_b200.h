@@ -133,6 +133,8 @@ int mv_gemm_bf16(const mv_gemm_args* args, void* stream);
  * waiting for an accumulator, [4] epilogue busy, [5] producer lifetime, [6] tiles; %globaltimer ns at [8] kernel entry,
  * [9] after the prologue / grid-dependency wait, [10] CTA end.  buf must hold 16 * 2 * num_sms int64. NULL disables. */
 void mv_gemm_set_profile_buffer(void* buf);
+/* Same idea for the attention forward (diagnostic build only): 16 int64 per CTA, layout in csrc/attention.cu. */
+void mv_attn_set_profile_buffer(void* buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm over channels of token rows (timm Block.norm1/norm2, final norm; eps 1e-6).

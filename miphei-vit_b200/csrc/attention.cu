@@ -38,7 +38,13 @@ struct AttnDev {
   __nv_bfloat16* out;
   long long ldo;
   float* lse;  // [B, heads, n_tok] or null (natural log)
+  long long* prof;  // diagnostics (MV_GEMM_PROFILE builds only): per CTA 16 x int64 cycle sums, see mv_attn_set_profile_buffer
 };
+
+#ifndef MV_GEMM_PROFILE
+#define MV_GEMM_PROFILE 0
+#endif
+constexpr bool kAttProf = MV_GEMM_PROFILE != 0;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -133,11 +139,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       const int ksteps = p.kb / 16;
       const int csplit_m = (p.kb / 32 + 1) >> 1;
+      long long pm_kv = 0, pm_p = 0;
+      const long long pm_t0 = kAttProf ? clock64() : 0;
       auto issue_s = [&](int s, int g) {
         const int it = g / nb, j = g - it * nb;
         const int qb = it & 1, st = g & 1;
+        const long long t_ = kAttProf ? clock64() : 0;
         if (j == 0) mbar_wait(bar(s, qb), (it >> 1) & 1);
         mbar_wait(bar(s, 4 + st), (g >> 1) & 1);
+        if (kAttProf) pm_kv += clock64() - t_;
         tc_fence_after();
         const uint64_t dq = umma_desc_sw128(sQ(s, qb));
         const uint64_t dk = umma_desc_sw128(sK(s, st));
@@ -150,7 +160,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       auto issue_pv = [&](int s, int g) {
         const int it = g / nb, j = g - it * nb;
         const int st = g & 1;
+        const long long t_ = kAttProf ? clock64() : 0;
         mbar_wait(bar(s, 9), g & 1);
+        if (kAttProf) pm_p += clock64() - t_;
         tc_fence_after();
         const uint32_t d = tmem_base + s * 256 + 128;
         const uint32_t a = tmem_base + s * 256;
@@ -175,6 +187,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
           }
         }
       }
+      if (kAttProf && p.prof) {
+        long long* q = p.prof + 16ll * blockIdx.x;
+        q[8] = pm_kv; q[9] = pm_p; q[10] = clock64() - pm_t0;
+      }
     }
   } else {
     // ===================== softmax warps =====================
@@ -194,6 +210,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     float* xs = xchg + s * (3 * 2 * 128);
     auto slot_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); };
     int g = 0;
+    long long pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // wait S | pass 1 | exchange barrier | rescale | pass 2 | st wait + arrive | item epilogue
+    const long long pa_t0 = kAttProf ? clock64() : 0;
+    long long pt = pa_t0;
+    auto lap = [&](int i) { if (kAttProf) { const long long n = clock64(); pa[i] += n - pt; pt = n; } };
     for (int it = 0; it < n_items[s]; ++it) {
       const int t = t0 + s + 2 * it;
       const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
@@ -201,6 +221,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       float m_ref = -INFINITY, l = 0.f;  // l: this thread's share of the row sum
       for (int j = 0; j < nb; ++j, ++g) {
         mbar_wait(bar(s, 8), g & 1);
+        lap(0);
         tc_fence_after();
         const int key0 = j * kb;
         const bool partial = key0 + kb > n_tok;  // block holds keys beyond the sequence: mask them
@@ -231,7 +252,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         // exchange with the row's other thread (buffer = block parity: the partner may already be one block ahead)
         float* xm = xs + (g & 1) * 256;
         xm[half * 128 + r] = mx;
+        lap(1);
         slot_bar();
+        lap(2);
         mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
         const float m_new = fmaxf(m_ref, mx * c);
         // ---- lazy rescale of the accumulator (warp-uniform decision: tcgen05.ld/st are warp collectives; both warps of
@@ -252,6 +275,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
           }
           m_ref = m_use;
         }
+        lap(3);
         // ---- pass 2: p = exp2(s*c - m_ref) -> bf16, written over S
         float sum = 0.f;
 #pragma unroll 1
@@ -291,9 +315,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
           tmem_st16(trow + 32 * csplit + 16 * (full32 - csplit), pk);  // upper 8 columns: dead (already read) part of S
         }
         l += sum;
+        lap(4);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar(s, 9));
+        lap(5);
       }
       // ---- epilogue of the item: O / l -> bf16 rows; row sum = both threads' shares
       float* xl = xs + 2 * 256;
@@ -321,6 +347,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         if (p.lse && half == 0) p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l_row)) * 0.6931471805599453f;
       }
       slot_bar();  // the sum buffer is reused by the next item
+      lap(6);
+    }
+    if (kAttProf && p.prof && warp == 2 && lane == 0) {
+      long long* q = p.prof + 16ll * blockIdx.x;
+      for (int i = 0; i < 7; ++i) q[i] = pa[i];
+      q[7] = clock64() - pa_t0;
+      q[11] = n_items[0] + n_items[1];
     }
   }
   tc_fence_before();
@@ -331,7 +364,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   }
 }
 
+static long long* g_attn_prof = nullptr;  // diagnostics only (mv_attn_set_profile_buffer)
+
 }  // namespace mv
+
+// Diagnostics (effective only in the MV_GEMM_PROFILE build): 16 int64 per CTA — softmax warp 2, lane 0: cycles [0] waiting for S,
+// [1] max pass, [2] row-max exchange barrier, [3] lazy rescale, [4] exp pass, [5] TMEM store wait + arrive, [6] item epilogue,
+// [7] lifetime; MMA thread: [8] waiting for Q / K|V, [9] waiting for P, [10] lifetime; [11] items of the CTA.
+extern "C" void mv_attn_set_profile_buffer(void* buf) { mv::g_attn_prof = reinterpret_cast<long long*>(buf); }
 
 // qkv bf16 [B*N, 3*D] rows = tokens (q | k | v, each heads x 64); out bf16 [B*N, D]; lse fp32 [B, heads, N] or NULL.
 extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, float* lse, int batch, int n_tok,
@@ -353,6 +393,7 @@ extern "C" int mv_attn_fwd(const void* qkv, int64_t ldqkv, void* out, int64_t ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
+  p.prof = g_attn_prof;
   const int smem = 12 * ATT_QBYTES + 256 + 2 * 3 * 2 * 128 * 4 + 1024;  // tiles, barriers, row-statistic exchange
   const uint64_t rows = (uint64_t)batch * n_tok;
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "mv_reset_launch_count": (None, []),
     "mv_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "mv_gemm_set_profile_buffer": (None, [c_void_p]),
+    "mv_attn_set_profile_buffer": (None, [c_void_p]),
     "mv_layernorm_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_float, c_void_p]),
     "mv_layernorm_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
