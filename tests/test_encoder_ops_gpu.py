@@ -44,7 +44,7 @@ def test_layernorm_fwd_bwd(M, D):
     assert (got2 - want2).abs().max().item() < 1e-4 * want2.abs().max().item() + 1e-5
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 329, 24), (1, 86, 2), (3, 128, 4), (2, 16, 1), (1, 384, 3), (2, 368, 2), (5, 329, 5), (2, 1301, 3), (1, 700, 2), (3, 129, 2), (1, 5334, 1), (2, 200, 2), (16, 329, 24)])
+@pytest.mark.parametrize("B,N,H", [(2, 329, 24), (1, 86, 2), (3, 128, 4), (2, 16, 1), (1, 384, 3), (2, 368, 2), (5, 329, 5), (2, 1301, 3), (1, 700, 2), (3, 129, 2), (1, 5334, 1), (2, 200, 2), (16, 329, 24), (1, 32, 2), (1, 48, 1), (2, 64, 2), (1, 40, 1), (1, 100, 1)])
 def test_attention_fwd(B, N, H):
     ops = _ops()
     D = H * 64

@@ -16,7 +16,7 @@ qkv = (torch.randn(B * N, 3 * H * 64, device="cuda") * 0.5).bfloat16()
 out = torch.empty(B * N, H * 64, dtype=torch.bfloat16, device="cuda")
 L = lib.init(0)
 buf = torch.zeros(16 * 2 * 148, dtype=torch.int64, device="cuda")
-for _ in range(3):
+for _ in range(300):  # also brings the SM clock up
     ops.attn_fwd(qkv, B, N, H, out=out)
 torch.cuda.synchronize()
 L.mv_attn_set_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
@@ -28,9 +28,11 @@ torch.cuda.synchronize()
 L.mv_attn_set_profile_buffer(ctypes.c_void_p(0))
 p = buf.view(-1, 16)[:148].double().cpu()
 life = p[:, 7].mean().item()
-names = ["wait S", "max pass", "exchange barrier", "lazy rescale", "exp pass", "st wait + arrive", "item epilogue"]
+names = ["wait S", "ld S + max", "exchange barrier", "wait PV + rescale", "exp pass", "st wait + arrive", "item epilogue"]
 print("B=%d N=%d: %.1f us; softmax warp (slot 0) lifetime %.0f cycles, %.1f items per CTA" % (B, N, e0.elapsed_time(e1) * 1e3, life, p[:, 11].mean().item()))
 for i, n in enumerate(names):
     print("  %-18s %8.0f cycles  %5.1f %%" % (n, p[:, i].mean().item(), 100 * p[:, i].mean().item() / life))
 ml = p[:, 10].mean().item()
-print("MMA thread lifetime %.0f cycles: waiting for Q / K|V %.1f %%, waiting for P %.1f %%" % (ml, 100 * p[:, 8].mean().item() / ml, 100 * p[:, 9].mean().item() / ml))
+print("MMA thread lifetime %.0f cycles: waiting for Q / K / V %.1f %%, for P %.1f %%, for the S columns %.1f %%"
+      % (ml, 100 * p[:, 8].mean().item() / ml, 100 * p[:, 9].mean().item() / ml, 100 * p[:, 12].mean().item() / ml))
+print("            issuing S MMAs + commits %.1f %%, issuing PV MMAs + commits %.1f %%" % (100 * p[:, 13].mean().item() / ml, 100 * p[:, 14].mean().item() / ml))
