@@ -332,20 +332,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       tmem_ld32(trow + 128 + half * 32, o);
       tmem_ld_wait();
       const int q = qt * 128 + r;
-      if (q < n_tok) {
-        const float inv = 1.f / l_row;
-        __nv_bfloat16* orow = p.out + (long long)(b * n_tok + q) * p.ldo + h * 64 + half * 32;
+      const float inv = 1.f / l_row;
+      uint4 oc[4];  // this thread's 32 output columns as four 16-byte chunks
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * jj + 0]) * inv, __uint_as_float(o[8 * jj + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * jj + 2]) * inv, __uint_as_float(o[8 * jj + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * jj + 4]) * inv, __uint_as_float(o[8 * jj + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * jj + 6]) * inv, __uint_as_float(o[8 * jj + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[jj] = u;
-        }
-        if (p.lse && half == 0) p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l_row)) * 0.6931471805599453f;
+      for (int jj = 0; jj < 4; ++jj) {
+        oc[jj].x = pack_bf16x2(__uint_as_float(o[8 * jj + 0]) * inv, __uint_as_float(o[8 * jj + 1]) * inv);
+        oc[jj].y = pack_bf16x2(__uint_as_float(o[8 * jj + 2]) * inv, __uint_as_float(o[8 * jj + 3]) * inv);
+        oc[jj].z = pack_bf16x2(__uint_as_float(o[8 * jj + 4]) * inv, __uint_as_float(o[8 * jj + 5]) * inv);
+        oc[jj].w = pack_bf16x2(__uint_as_float(o[8 * jj + 6]) * inv, __uint_as_float(o[8 * jj + 7]) * inv);
       }
+      // four neighbouring lanes write one row's 64 bytes (profiles/r02_attention_fwd_experiments.txt: the row-per-lane
+      // stores, 32 rows x 16 bytes per instruction, were 18 % of the kernel)
+      lane4_transpose_u4(oc, lane);
+      {
+        const int qw = qt * 128 + quad * 32 + (lane & ~3);  // first of this lane group's four rows
+        __nv_bfloat16* obase = p.out + (long long)(b * n_tok + qw) * p.ldo + h * 64 + half * 32 + (lane & 3) * 8;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (qw + jj < n_tok) *reinterpret_cast<uint4*>(obase + (long long)jj * p.ldo) = oc[jj];
+      }
+      if (q < n_tok && p.lse && half == 0)
+        p.lse[((long long)b * p.heads + h) * n_tok + q] = (m_ref + log2f(l_row)) * 0.6931471805599453f;
       slot_bar();  // the sum buffer is reused by the next item
       lap(6);
     }

@@ -283,18 +283,23 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty);
-      if (orow < n_tok) {
-        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + orow) * p.lddqkv + h * 64 + half * 32;
+      {
+        // four neighbouring lanes write one row's 64 bytes (8 rows per store instruction, not 32 rows of 16 bytes)
+        const int row4 = ob * 128 + quad * 32 + (lane & ~3);  // first of this lane group's four rows
+        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + row4) * p.lddqkv + h * 64 + half * 32 + (lane & 3) * 8;
         auto store32 = [&](__nv_bfloat16* dst, const uint32_t* v, float mul) {
+          uint4 c[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
-            u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
-            u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
-            u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
-            reinterpret_cast<uint4*>(dst)[j] = u;
+            c[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
+            c[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
+            c[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
+            c[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
           }
+          lane4_transpose_u4(c, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (row4 + j < n_tok) *reinterpret_cast<uint4*>(dst + (long long)j * p.lddqkv) = c[j];
         };
         if (DKV) {
           store32(base + p.dim, a0, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)

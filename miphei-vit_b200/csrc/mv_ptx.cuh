@@ -301,6 +301,27 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t u) {
   }
   return unpack_bf16x2(u);
 }
+// 4 x 4 transpose of 16-byte elements inside every group of four consecutive lanes: on entry lane 4g+t holds a[0..3] = the
+// four 16-byte chunks of ITS row; on exit it holds chunk t of rows 4g+0..3 (a[j] = chunk t of row 4g+j).  A row-per-lane
+// epilogue (tcgen05.ld 32x32b gives every thread one accumulator row) can then store 64 contiguous bytes per row from four
+// neighbouring lanes — 8 rows per store instruction instead of 32 rows of 16 bytes each (4x fewer LSU wavefronts).
+__device__ __forceinline__ void lane4_transpose_u4(uint4 (&a)[4], int lane) {
+  auto xchg = [&](uint4& keep_lo, uint4& keep_hi, int bit) {
+    // lanes with the bit clear keep keep_lo and receive the partner's keep_lo into keep_hi; lanes with it set the reverse
+    const bool hi = (lane & bit) != 0;
+    uint4 send = hi ? keep_lo : keep_hi, recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, bit);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, bit);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, bit);
+    recv.w = __shfl_xor_sync(0xffffffffu, send.w, bit);
+    if (hi) keep_lo = recv; else keep_hi = recv;
+  };
+  xchg(a[0], a[1], 1);
+  xchg(a[2], a[3], 1);
+  xchg(a[0], a[2], 2);
+  xchg(a[1], a[3], 2);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
