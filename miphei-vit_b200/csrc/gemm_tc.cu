@@ -29,6 +29,15 @@ constexpr int MV_GEMM_LINEAR_TMA = 16;
 // internal mode: LINEAR with bf16 output, no residual (QKV, the dX GEMMs): accumulator -> scale / shift (/ ReLU) -> bf16 ->
 // swizzled shared-memory tile -> one TMA store per 32 rows x 64 columns; no transpose staging, no per-thread global store
 constexpr int MV_GEMM_LINEAR_TMA_BF16 = 17;
+// the same epilogue with EIGHT epilogue warps (two per TMEM lane quadrant, every other 64-column chunk each) and the
+// GATE_MASK activation: problems of one or two K blocks over millions of rows (the decoder's 32-channel maps at 256^2) are
+// bound by how fast the accumulators leave TMEM.  The transpose-staging epilogue of the 128-wide "light" tiles executed
+// ~2500 warp instructions per 128 x 128 tile on 2 warps per scheduler (ncu source page, profiles/r02_skinny_k_gemm.txt):
+// e = mask(f W1^T) [2M x 256] took 1130 us for 1 GB of output.
+constexpr int MV_GEMM_LINEAR_TMA_BF16_W8 = 18;
+__host__ __device__ constexpr bool gemm_tma_bf16(int mode) {
+  return mode == MV_GEMM_LINEAR_TMA_BF16 || mode == MV_GEMM_LINEAR_TMA_BF16_W8;
+}
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
@@ -44,7 +53,7 @@ constexpr bool kProf = MV_GEMM_PROFILE != 0;
 #define MV_LINEAR_EPI_WARPS 4  // 8 spills on the fp32 + residual path (204-register cap) and loses 30-50 % there
 #endif
 __host__ __device__ constexpr int gemm_epi_warps(int mode, int block_n, bool light) {
-  return (mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD) ? 8
+  return (mode == MV_GEMM_SWIGLU || mode == MV_GEMM_SWIGLU_BWD || mode == MV_GEMM_LINEAR_TMA_BF16_W8) ? 8
          : (mode == MV_GEMM_LINEAR && block_n >= 128 && !light) ? MV_LINEAR_EPI_WARPS : 4;
 }
 __host__ __device__ constexpr int gemm_threads(int mode, int block_n, bool light) {
@@ -155,11 +164,13 @@ struct GemmCfg {
   static constexpr int kBBytes = kRowsB * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = gemm_epi_warps(MODE, BLOCK_N, LIGHT);
-  static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA || MODE == MV_GEMM_LINEAR_TMA_BF16;
+  static constexpr bool kEpiTma = MODE == MV_GEMM_LINEAR_TMA || gemm_tma_bf16(MODE);
   // LINEAR_TMA: per epilogue warp kTmaResStages residual tiles + kTmaOutStages output tiles of 32 rows x 32 fp32 columns
   // (4 KB each, 128-byte swizzle, 1 KB aligned) directly behind the operand ring; the transpose staging is not needed there
   static constexpr int kTmaResStages = MODE == MV_GEMM_LINEAR_TMA ? MV_TMA_RES_STAGES : 0;
-  static constexpr int kTmaOutStages = MODE == MV_GEMM_LINEAR_TMA ? MV_TMA_OUT_STAGES_F32 : MV_TMA_OUT_STAGES_BF16;
+  // (the eight-warp skinny-K form is bound by its epilogue: a second output tile per warp lets a store drain under the next chunk)
+  static constexpr int kTmaOutStages = MODE == MV_GEMM_LINEAR_TMA ? MV_TMA_OUT_STAGES_F32
+                                       : MODE == MV_GEMM_LINEAR_TMA_BF16_W8 ? 2 : MV_TMA_OUT_STAGES_BF16;
   static constexpr int kEpiTmaBytes = kEpiTma ? kEpiWarps * (kTmaResStages + kTmaOutStages) * 4096 : 0;
   static constexpr int kStagingBytes = kEpiTma ? 0 : kEpiWarps * 32 * 36 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (padded rows)
   static constexpr int kStatBytes = 2 * 256 * 4;         // CTA-level per-column (sum, sumsq) accumulators
@@ -632,6 +643,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       if constexpr (MODE == MV_GEMM_SWIGLU_BWD) load_h(egrp, hgn, hvn);
+      // skinny-K TMA epilogue with GATE_MASK: this row's gate gradients for every chunk this warp converts (4 heads = 8 bytes
+      // per 64-column chunk), requested before the accumulator is awaited
+      constexpr int kDuChunks = MODE == MV_GEMM_LINEAR_TMA_BF16_W8 ? (BLOCK_N / 64 + EGRPS - 1) / EGRPS : 1;
+      uint2 du_row[kDuChunks];
+      if constexpr (MODE == MV_GEMM_LINEAR_TMA_BF16_W8) {
+#pragma unroll
+        for (int i = 0; i < kDuChunks; ++i) {
+          du_row[i] = make_uint2(0u, 0u);
+          const int c0_ = n_blk * BLOCK_N + (egrp + i * EGRPS) * 64;
+          if (p.act == MV_ACT_GATE_MASK && row_ok && c0_ < p.n)
+            du_row[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.in2) + (long long)m * p.ldin2 + (c0_ >> 4));
+        }
+      }
       // GATE_MASK (heads backward, 128-wide two-CTA-per-SM tiles): the per-(row, head) gate gradients of the WHOLE tile are
       // fetched before the accumulator wait — this epilogue-bound kernel otherwise exposes their latency once per chunk
       constexpr bool kPreloadDu = MODE == MV_GEMM_LINEAR && LIGHT && BLOCK_N == 128;
@@ -942,19 +966,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_commit();
           }
         }
-      } else if constexpr (MODE == MV_GEMM_LINEAR_TMA_BF16) {
+      } else if constexpr (gemm_tma_bf16(MODE)) {
         // out = act(acc * scale + shift) in bf16: 32 rows x 64 columns (128-byte rows) per step and warp, written row per lane
         // into the 128-byte-swizzled tile a TMA store expects; output stages alternate so that a store drains while the next
-        // chunk is converted.
+        // chunk is converted.  With eight epilogue warps the two warps of a lane quadrant take every other chunk.
         constexpr int NC = BLOCK_N / 64;
         const int m_warp = m_blk * GEMM_BLOCK_M + quad * 32;
         const int swz = lane & 7;
         const bool relu = p.act == MV_ACT_RELU;
+        const bool gmask = p.act == MV_ACT_GATE_MASK;
+        const int n0 = n_blk * BLOCK_N;
+        // chunks that start beyond N hold nothing (N = 144 on a 256-wide tile): never loaded, converted or stored
+        auto live = [&](int c_) { return c_ < NC && n0 + c_ * 64 < p.n; };
         uint32_t v0[32], v1[32];
-        acc_ld32(0, v0);
-        acc_ld32(32, v1);
+        if (live(egrp)) {
+          acc_ld32(egrp * 64, v0);
+          acc_ld32(egrp * 64 + 32, v1);
+        }
 #pragma unroll 1
-        for (int c = 0; c < NC; ++c) {
+        for (int c = egrp; live(c); c += EGRPS) {
+          // GATE_MASK: out = du[row, column / 16] where the unit is active — the row's four gate gradients of this chunk
+          uint2 dug = make_uint2(0u, 0u);
+          if constexpr (MODE == MV_GEMM_LINEAR_TMA_BF16_W8) {
+#pragma unroll
+            for (int i = 0; i < kDuChunks; ++i)
+              if (c == egrp + i * EGRPS) dug = du_row[i];
+          }
           acc_wait();
           uint32_t pk[32];  // 64 bf16
 #pragma unroll
@@ -967,24 +1004,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float f0 = fmaf(__uint_as_float(vv[4 * j + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(vv[4 * j + 1]), sc.y, sh.y);
               float f2 = fmaf(__uint_as_float(vv[4 * j + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(vv[4 * j + 3]), sc.w, sh.w);
               if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+              if (gmask) {  // columns 32 h + 4 j .. + 3 belong to head (2 h + j / 4) of the chunk's four
+                const uint32_t w = h ? dug.y : dug.x;
+                const float du = __uint_as_float(j < 4 ? (w << 16) : (w & 0xffff0000u));
+                f0 = f0 > 0.f ? du : 0.f; f1 = f1 > 0.f ? du : 0.f; f2 = f2 > 0.f ? du : 0.f; f3 = f3 > 0.f ? du : 0.f;
+              }
               pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
               pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
             }
           }
-          if (c + 1 < NC) {
-            acc_ld32((c + 1) * 64, v0);
-            acc_ld32((c + 1) * 64 + 32, v1);
+          if (live(c + EGRPS)) {
+            acc_ld32((c + EGRPS) * 64, v0);
+            acc_ld32((c + EGRPS) * 64 + 32, v1);
           }
+          const int oslot = (c / EGRPS) % TO;
           if (lane == 0) tma_store_wait_read<TO - 1>();  // the store that last used this output stage has drained it
           __syncwarp();
-          uint8_t* os = tma_epi_gen + (c % TO) * 4096 + lane * 128;
+          uint8_t* os = tma_epi_gen + oslot * 4096 + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(os + ((j ^ swz) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_o, tma_epi_base + (c % TO) * 4096u, n_blk * BLOCK_N + c * 64, m_warp);
+            tma_store_2d(&tmap_o, tma_epi_base + oslot * 4096u, n0 + c * 64, m_warp);
             tma_store_commit();
           }
         }
@@ -1309,7 +1352,7 @@ static int launch_gemm(const mv_gemm_args& a, cudaStream_t stream, int tile_limi
     tr = get_tmap_2d_f32(a.resid, a.m, a.n, a.ldr, 32);
     to = get_tmap_2d_f32(a.out, a.m, a.n, a.ldo, 32);
     if (!tr || !to) return MV_ERR_ARG;
-  } else if (MODE == MV_GEMM_LINEAR_TMA_BF16) {
+  } else if (gemm_tma_bf16(MODE)) {
     to = get_tmap_2d_bf16(a.out, a.m, a.n, a.ldo, 32, 64);
     if (!to) return MV_ERR_ARG;
   }
@@ -1535,6 +1578,18 @@ extern "C" int mv_gemm_bf16(const mv_gemm_args* args, void* stream_) {
           if (cost(128, 1.25) < best) { best = cost(128, 1.25); bn = 128; }
           if (a.n % 256 != 0 && bn == 256 && a.n % 128 == 0 && a.n < 256) bn = 128;
         }
+      }
+      {
+        // one or two K blocks, more than 128 bf16 output columns, many rows: CTA pairs on 256-wide tiles whose eight epilogue
+        // warps hand 32 x 64 tiles to TMA stores (MV_GEMM_SKINNY_TMA=0 keeps the 128-wide two-CTA-per-SM schedule)
+        static const int skinny_env = [] { const char* e = getenv("MV_GEMM_SKINNY_TMA"); return e ? atoi(e) : 1; }();
+        const int kb_ = (a.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+        if (skinny_env != 0 && a.block_n == 0 && pair_legal && a.reserved2 != 1 && kb_ <= 2 && a.n > 128 && a.m >= 4096 &&
+            a.out_f32 == 0 && a.out && !a.resid && !a.aux && !a.colstats && a.rows_per_group == 0 && a.kskip_end == 0 &&
+            a.ldo % 8 == 0 &&
+            (a.act == MV_ACT_NONE || a.act == MV_ACT_RELU ||
+             (a.act == MV_ACT_GATE_MASK && a.in2 && a.ldin2 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in2) & 7) == 0)))
+          return launch_gemm<256, MV_GEMM_LINEAR_TMA_BF16_W8, true>(a, stream);
       }
       {
         // epilogue-bound shapes (one or two K blocks, or a narrow N over many rows): two CTAs per SM

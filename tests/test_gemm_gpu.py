@@ -250,6 +250,40 @@ def test_gemm_bf16_out_tma_epilogue(M, N, K):
     assert float((big[:, 8 + N:].float() - 3).abs().max()) == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 256, 32), (5000, 144, 32), (4100, 256, 64), (6000, 200, 96), (70000, 144, 32)])
+def test_gemm_skinny_k_tma_epilogue(M, N, K):
+    """One or two K blocks over many rows (the decoder's 32-channel maps): CTA pairs, eight epilogue warps, TMA stores.
+    Must agree bit for bit with the register epilogue of the 128-wide tiles (pair=1 keeps that schedule), N tails included."""
+    ops = _ops()
+    a = _rand((M, K), 1.0, 1).bfloat16()
+    w = _rand((N, K), 0.2, 2).bfloat16()
+    scale, shift = 1 + _rand((N,), 0.1, 3), _rand((N,), 0.3, 4)
+    ref = (a.float() @ w.float().t()) * scale + shift
+    for act in (ops.ACT_NONE, ops.ACT_RELU):
+        r = torch.relu(ref) if act == ops.ACT_RELU else ref
+        old = ops.gemm(a, w, scale=scale, shift=shift, act=act, pair=1)
+        new = ops.gemm(a, w, scale=scale, shift=shift, act=act)
+        _close(new, r, 1e-2)
+        assert torch.equal(old, new)
+    plain = ops.gemm(a, w)
+    assert torch.equal(plain, ops.gemm(a, w, pair=1))
+    if N % 16 == 0:  # GATE_MASK: out[m, n] = du[m, n / 16] where the unit is active
+        du = _rand((M, N // 16), 1.0, 5).bfloat16()
+        dup = torch.zeros((M, 16), dtype=torch.bfloat16, device="cuda")
+        dup[:, :N // 16] = du
+        old = ops.gemm(a, w, scale=scale, shift=shift, act=ops.ACT_GATE_MASK, in2=dup, pair=1)
+        new = ops.gemm(a, w, scale=scale, shift=shift, act=ops.ACT_GATE_MASK, in2=dup)
+        assert torch.equal(old, new)
+        want = torch.where(ref > 0, du.float().repeat_interleave(16, dim=1), torch.zeros_like(ref))
+        assert ((new.float() - want).abs() > 1e-6).float().mean().item() < 2e-3  # sign flips at rounding level only
+    big = torch.full((M + 8, N + 24), 3.0, dtype=torch.bfloat16, device="cuda")   # strided output view, guard band untouched
+    view = big[8:, 8:8 + N]
+    ops.gemm(a, w, shift=shift, out=view)
+    _close(view, a.float() @ w.float().t() + shift, 1e-2)
+    assert float((big[:8].float() - 3).abs().max()) == 0 and float((big[:, :8].float() - 3).abs().max()) == 0
+    assert float((big[:, 8 + N:].float() - 3).abs().max()) == 0
+
+
 @pytest.mark.parametrize("M,N,K", [(10528, 1536, 1536), (10528, 1536, 4096), (5264, 4608, 1536), (4000, 768, 256)])
 def test_gemm_tail_retiling(M, N, K):
     """optional schedule of the big CTA-pair GEMMs (measured slower, off by default): full waves of 256 x 256 tiles, then the
