@@ -293,6 +293,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  // pair, non-leader CTA: its epilogue warps release an accumulator stage on this LOCAL barrier; one otherwise idle thread
+  // forwards the release to the leader (the remote arrival needs cluster-scope release semantics, which compile to
+  // MEMBAR.ALL.GPU + ERRBAR: 13 % of the stall samples of an epilogue-bound kernel when every epilogue warp paid for it)
+  auto tfwd_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kRingEnd + 8 * (2 * STAGES + 4));
@@ -315,8 +319,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      // one arrival per epilogue warp (pair: the peer's warps arrive remotely)
-      mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * Cfg::kEpiWarps);
+      // one arrival per epilogue warp (pair: plus one for the peer CTA, forwarded by its idle MMA-warp thread)
+      mbar_init(tempty_bar(s), Cfg::kEpiWarps + (PAIR ? 1 : 0));
+      mbar_init(tfwd_bar(s), Cfg::kEpiWarps);
     }
     if constexpr (Cfg::kEpiTma) {
 #pragma unroll
@@ -533,6 +538,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+    if (PAIR && lane == 0 && !leader) {
+      // ---- peer CTA: forward "accumulator stage released" from this CTA's epilogue warps to the leader's MMA thread
+      SegIter it(p, tile_start, tile_step);
+      int tile, kb0, kb1, as = 0;
+      uint32_t fph = 0;
+      bool partial;
+      while (it.next(tile, kb0, kb1, partial)) {
+        mbar_wait(tfwd_bar(as), fph);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive_cluster(tempty_bar(as), 0);
+        if (++as == 2) { as = 0; fph ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
     const int quad = warp & 3;
@@ -566,7 +585,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tma_epi_base = smem_base + STAGES * Cfg::kStageBytes + (uint32_t)ew * (TR + TO) * 4096u;
     uint8_t* tma_epi_gen = smem_gen + STAGES * Cfg::kStageBytes + (size_t)ew * (TR + TO) * 4096;
     auto rbar = [&](int s_) { return bar_base + 256u + 8u * (uint32_t)(ew * TR + s_); };
-    uint32_t tma_issued = 0, tma_waited = 0;
+    uint32_t tma_issued = 0, tma_waited = 0, tma_stores = 0;
     SegIter it(p, tile_start, tile_step);
     int tile, kb0_, kb1_;
     bool partial;
@@ -713,7 +732,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {  // the accumulator stage is free again
-            if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+            if (PAIR && !leader) mbar_arrive(tfwd_bar(as)); else mbar_arrive(tempty_bar(as));
           }
           __threadfence();
           ep_bar();
@@ -1017,7 +1036,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             acc_ld32((c + EGRPS) * 64, v0);
             acc_ld32((c + EGRPS) * 64 + 32, v1);
           }
-          const int oslot = (c / EGRPS) % TO;
+          const int oslot = (int)(tma_stores++ % (uint32_t)TO);  // running count: a warp may convert ONE chunk per tile (N = 144)
           if (lane == 0) tma_store_wait_read<TO - 1>();  // the store that last used this output stage has drained it
           __syncwarp();
           uint8_t* os = tma_epi_gen + oslot * 4096 + lane * 128;
@@ -1270,7 +1289,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0 && !from_ws) {  // (a stream-K finisher released its accumulator stage before the counter)
-        if (PAIR && !leader) mbar_arrive_cluster(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+        if (PAIR && !leader) mbar_arrive(tfwd_bar(as)); else mbar_arrive(tempty_bar(as));
       }
       if (kProf && p.prof && warp == 2) {
         prof_acc[3] += te1_ - te0_;

@@ -46,7 +46,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Arrive on the same-offset barrier of another CTA in the cluster (used by CTA pairs).
+// Arrive on the same-offset barrier of another CTA in the cluster (used by CTA pairs: "this accumulator stage has been
+// read").  The cluster-scope release is required: with the default CTA-scope form the leader's MMAs overwrote accumulators
+// the peer was still reading (4 of 16 runs of tests/test_gemm_gpu.py failed, tools/stress_gemm_tests.py).  It compiles to
+// MEMBAR.ALL.GPU + ERRBAR, so the GEMM kernel issues it from ONE forwarding thread per tile, not from every epilogue warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"

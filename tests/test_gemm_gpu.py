@@ -250,7 +250,7 @@ def test_gemm_bf16_out_tma_epilogue(M, N, K):
     assert float((big[:, 8 + N:].float() - 3).abs().max()) == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(8192, 256, 32), (5000, 144, 32), (4100, 256, 64), (6000, 200, 96), (70000, 144, 32)])
+@pytest.mark.parametrize("M,N,K", [(8192, 256, 32), (5000, 144, 32), (4100, 256, 64), (6000, 200, 96), (70000, 144, 32), (1048576, 144, 32)])
 def test_gemm_skinny_k_tma_epilogue(M, N, K):
     """One or two K blocks over many rows (the decoder's 32-channel maps): CTA pairs, eight epilogue warps, TMA stores.
     Must agree bit for bit with the register epilogue of the 128-wide tiles (pair=1 keeps that schedule), N tails included."""
