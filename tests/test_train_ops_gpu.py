@@ -51,9 +51,10 @@ def test_gemm_nn_atomic(M, N, K):
     assert (out - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
-def test_lora_grads():
+@pytest.mark.parametrize("M,D", [(1000, 256), (10528, 1536), (37, 128), (5000, 512), (2 * 329, 1024), (700, 320)])
+def test_lora_grads(M, D):
+    """mma.sync path for the widths it is instantiated for (D / 64 in {2, 4, 6, 8, 12, 16, 24}), split-K tcgen05 GEMMs otherwise"""
     ops = _ops()
-    M, D = 1000, 256
     xn_ext = _rand((M, D + 64), 1.0, 1).bfloat16()
     dq_ext = _rand((M, 3 * D + 64), 1.0, 2).bfloat16()
     dAq, dAv = torch.zeros(D, 8, device="cuda"), torch.zeros(D, 8, device="cuda")
