@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       mbar_init(c_empty(s), 1);
     }
     mbar_init(bar_xy, 1);
-    mbar_init(bar_pd, 256);
+    mbar_init(bar_pd, 8);      // one arrival per math warp
     mbar_init(bar_acc, 1);
-    mbar_init(acc_empty, 256);
+    mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         tmem_st16(trow + COL_Y + half * 32, pd);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(bar_pd);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pd);  // 8 arrivals, not 256 serialised updates of one shared-memory word
         xph ^= 1;
       }
       // ---- epilogue: accumulators -> bf16 rows of dqkv
@@ -282,7 +283,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       if (DKV) tmem_ld32(trow + COL_A1 + half * 32, b0);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(acc_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
       {
         // four neighbouring lanes write one row's 64 bytes (8 rows per store instruction, not 32 rows of 16 bytes)
         const int row4 = ob * 128 + quad * 32 + (lane & ~3);  // first of this lane group's four rows
