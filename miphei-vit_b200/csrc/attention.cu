@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   }
 }
 
-static long long* g_attn_prof = nullptr;  // diagnostics only (mv_attn_set_profile_buffer)
+long long* g_attn_prof = nullptr;  // diagnostics only (mv_attn_set_profile_buffer); also read by attention_bwd.cu
 
 }  // namespace mv
 

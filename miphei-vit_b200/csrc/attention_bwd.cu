@@ -36,7 +36,14 @@ struct AttnBwdDev {
   const float* dsum;   // [B, heads, n_tok]
   __nv_bfloat16* dqkv; // [B*n_tok, 3*dim]
   long long lddqkv;
+  long long* prof;     // diagnostics (MV_GEMM_PROFILE builds only): per CTA 16 x int64 cycle sums, see tools/attn_roles.py
 };
+
+#ifndef MV_GEMM_PROFILE
+#define MV_GEMM_PROFILE 0
+#endif
+constexpr bool kAtbProf = MV_GEMM_PROFILE != 0;
+extern long long* g_attn_prof;
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -67,8 +74,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
                  acc_empty = bar_base + 8u * 9;
   const uint32_t tmem_slot = bar_base + 8u * 10;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 10);
-  float* s_lse = reinterpret_cast<float*>(smem_gen + misc_off + 128);  // [2][64] (scaled by log2e)
-  float* s_dsum = s_lse + 128;                                          // [2][64]
+  // DKV: per-column (query) statistics of the current inner tile, one private copy per math warp: [8][lse * log2e 64 | D 64]
+  float* s_stat = reinterpret_cast<float*>(smem_gen + misc_off + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = (int)((long long)p.total_items * blockIdx.x / gridDim.x);
@@ -150,10 +157,15 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
       const uint64_t dk1 = umma_desc_sw128(sC), dk2 = umma_desc_sw128(sC + ATB_CTILE);                            // K-major
       const uint64_t dm1 = umma_desc_sw128(sC, 1024, 1024), dm2 = umma_desc_sw128(sC + ATB_CTILE, 1024, 1024);  // MN-major
       constexpr uint64_t kStageStep = (2 * ATB_CTILE) >> 4;
+      long long pm[4] = {0, 0, 0, 0};  // waiting for operands | issuing XY | waiting for P, dS | issuing the accumulations
+      const long long pm_t0 = kAtbProf ? clock64() : 0;
+      long long pt = pm_t0;
+      auto lap = [&](int i) { if (kAtbProf) { const long long n = clock64(); pm[i] += n - pt; pt = n; } };
       for (int t = t0; t < t1; ++t) {
         mbar_wait(r_full, rph);
         for (int ib = 0; ib < ncb; ++ib) {
           mbar_wait(c_full(cs), cph);
+          lap(0);
           tc_fence_after();
           const uint64_t so = cs ? kStageStep : 0;
           const uint64_t dc1 = dk1 + so, dc2 = dk2 + so;
@@ -162,8 +174,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_Y, dr2 + 2 * k, dc2 + 2 * k, idesc_xy, k != 0);
           umma_commit(bar_xy);
+          lap(1);
           mbar_wait(bar_pd, xph);
           if (ib == 0) mbar_wait(acc_empty, aph ^ 1);  // previous item's accumulators drained
+          lap(2);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile; 16 reduction rows = 2 KB per step
@@ -179,9 +193,14 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
           }
           if (++cs == 2) { cs = 0; cph ^= 1; }
           xph ^= 1;
+          lap(3);
         }
         rph ^= 1;
         aph ^= 1;
+      }
+      if (kAtbProf && p.prof) {
+        long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));  // dK/dV instance first, dQ instance behind
+        q[8] = pm[0]; q[9] = pm[1]; q[10] = pm[2]; q[11] = pm[3]; q[12] = clock64() - pm_t0;
       }
     }
   } else {
@@ -194,6 +213,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
     const int n_tok = p.n_tok;
     uint32_t xph = 0, aph = 0;
     int itn = 0;
+    long long pa[6] = {0, 0, 0, 0, 0, 0};  // statistics staging | wait X, Y | ld + math | st + arrive | item epilogue
+    const long long pa_t0 = kAtbProf ? clock64() : 0;
+    long long pt = pa_t0;
+    auto lap = [&](int i) { if (kAtbProf) { const long long n = clock64(); pa[i] += n - pt; pt = n; } };
     for (int t = t0; t < t1; ++t) {
       const int bh = t / nrb, ob = t - bh * nrb;
       const int b = bh / p.heads, h = bh - b * p.heads;
@@ -204,24 +227,37 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
         dsum_r = p.dsum[vec0 + orow];
       }
-      // DKV: per-column (query) statistics of an inner tile — threads 0..63 carry lse * log2(e), threads 64..127 D — are
-      // fetched ONE TILE AHEAD into a register, so the global-load latency is not on the per-tile critical path
-      auto load_stat = [&](int ib) {
-        const int q = ib * 64 + (tid & 63);
-        if (q >= n_tok || tid >= 128) return 0.f;
-        return tid < 64 ? p.lse[vec0 + q] * 1.4426950408889634f : p.dsum[vec0 + q];
+      // DKV: per-column (query) statistics of an inner tile: every warp keeps its own copy (lane l fetches queries l and
+      // l + 32, lse and D) ONE TILE AHEAD into registers and parks it in its private smem row — no CTA-wide barrier per tile.
+      // (Measured neutral against the shared copy behind a named barrier, 213 vs 215 us at B = 32: the time a math warp
+      // spends here, ~0.9 k of 4.8 k cycles per tile pair in tools/attn_bwd_roles.py, moves into "wait X, Y" — the tile
+      // pair is a serial chain  math -> accumulate MMAs -> next X, Y MMAs  and only the SM's second CTA overlaps it.)
+      float* my_stat = s_stat + (warp - 2) * 128;
+      // RAW loads with clamped indices and no arithmetic or select on the result: a warp issues in order, so anything that
+      // consumes the loaded value here would stall it for the whole L2 round trip; queries beyond the sequence are masked
+      // in the math
+      auto load_stat = [&](int ib, float (&v)[4]) {
+        const int q0 = min(ib * 64 + lane, n_tok - 1), q1 = min(ib * 64 + 32 + lane, n_tok - 1);
+        v[0] = __ldg(p.lse + vec0 + q0);
+        v[1] = __ldg(p.lse + vec0 + q1);
+        v[2] = __ldg(p.dsum + vec0 + q0);
+        v[3] = __ldg(p.dsum + vec0 + q1);
       };
-      float stat_next = DKV ? load_stat(0) : 0.f;
+      float stat_next[4] = {0.f, 0.f, 0.f, 0.f};
+      if (DKV) load_stat(0, stat_next);
       for (int ib = 0; ib < ncb; ++ib, ++itn) {
-        const float* sl = s_lse + (itn & 1) * 64;
-        const float* sd = s_dsum + (itn & 1) * 64;
-        if (DKV) {  // double-buffered smem copy of this tile's statistics
-          if (tid < 64) s_lse[(itn & 1) * 64 + tid] = stat_next;
-          else if (tid < 128) s_dsum[(itn & 1) * 64 + tid - 64] = stat_next;
-          nbar(1, 256);
-          if (ib + 1 < ncb) stat_next = load_stat(ib + 1);
+        const float* sl = my_stat;
+        const float* sd = my_stat + 64;
+        if (DKV) {
+          __syncwarp();  // every lane has finished reading the previous tile's copy
+          my_stat[lane] = stat_next[0] * 1.4426950408889634f; my_stat[32 + lane] = stat_next[1] * 1.4426950408889634f;
+          my_stat[64 + lane] = stat_next[2]; my_stat[96 + lane] = stat_next[3];
+          __syncwarp();
+          if (ib + 1 < ncb) load_stat(ib + 1, stat_next);
         }
+        lap(0);
         mbar_wait(bar_xy, xph);
+        lap(1);
         tc_fence_after();
         // this thread's 32 columns [32*half, 32*half+32) of X and Y: one TMEM round trip; P / dS (bf16 pairs) go back into
         // the first 16 columns of the SAME range, so the two threads of a row never touch each other's columns
@@ -267,6 +303,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
             pd[j] = pack_bf16x2(dv[0], dv[1]);
           }
         }
+        lap(2);
         if (DKV) tmem_st16(trow + COL_X + half * 32, pp);
         tmem_st16(trow + COL_Y + half * 32, pd);
         tmem_st_wait();
@@ -274,6 +311,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pd);  // 8 arrivals, not 256 serialised updates of one shared-memory word
         xph ^= 1;
+        lap(3);
       }
       // ---- epilogue: accumulators -> bf16 rows of dqkv
       mbar_wait(bar_acc, aph);
@@ -311,6 +349,13 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
         }
       }
       aph ^= 1;
+      lap(4);
+    }
+    if (kAtbProf && p.prof && warp == 2 && lane == 0) {
+      long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));  // dK/dV instance first, dQ instance behind
+      for (int i = 0; i < 5; ++i) q[i] = pa[i];
+      q[5] = clock64() - pa_t0;
+      q[6] = (t1 - t0) * ncb;
     }
   }
   tc_fence_before();
@@ -383,12 +428,13 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   p.dsum = dsum;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.lddqkv = lddqkv;
+  p.prof = g_attn_prof;
   const CUtensorMap* tq = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 128);
   const CUtensorMap* td = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 128);
   const CUtensorMap* tq64 = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 64);
   const CUtensorMap* td64 = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 64);
   if (!tq || !td || !tq64 || !td64) return MV_ERR_ARG;
-  const int smem = 2 * ATB_RTILE + 4 * ATB_CTILE + 128 + 4 * 64 * 4 + 1024;
+  const int smem = 2 * ATB_RTILE + 4 * ATB_CTILE + 128 + 8 * 128 * 4 + 1024;
   static std::atomic<uint64_t> attr{0};  // one bit per device
   if (first_use_on_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
