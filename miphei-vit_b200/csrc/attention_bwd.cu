@@ -15,6 +15,8 @@
 // X into P and Y into dS (bf16, written back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A
 // operand read from TMEM and the C tiles re-read from the SAME smem tiles as MN-major operands.  Two CTAs are resident per
 // SM (64 KB smem, 256 TMEM columns each), so one CTA's exponentials overlap the other CTA's MMAs.
+#include <stdlib.h>
+
 #include "mv_host.h"
 #include "mv_ptx.cuh"
 
@@ -366,6 +368,335 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Version 2 of the same kernel pair: ONE CTA per SM owning all 512 TMEM columns, X / Y TRIPLE-buffered, two MMA threads.
+// In version 1 a tile pair is a serial chain inside its CTA (X, Y MMAs -> math -> accumulate MMAs -> next X, Y MMAs; P / dS
+// alias X / Y, so the next X, Y cannot start before the accumulations have consumed them) and only the SM's second CTA fills
+// the gaps: tools/attn_bwd_roles.py shows a math warp waiting for X, Y 22 % (dK/dV) / 47 % (dQ) of its life and the MMA thread
+// waiting for P / dS 50-58 % of its.  Here tile n+3's X, Y go into the buffer tile n's accumulations free, so the X, Y of the
+// next tiles are complete long before the math of tile n ends; the row operands (128 keys or queries) have two smem stages
+// and the column tiles six.  One issuing thread needs ~100 cycles per MMA (waits, commits, descriptors): with 16 MMAs per tile
+// pair a single issuer was the bound (first cut of this version: 241 us against 215 us for version 1 at B = 32), so the X, Y
+// products and the accumulations have a thread each; "buffer free" travels between them as a commit barrier.
+//   TMEM: X0 0 | Y0 64 | X1 128 | Y1 192 | X2 256 | Y2 320 | acc1 384 | acc2 448   (tile n uses buffer n % 3; P / dS alias X / Y)
+constexpr int ATB2_THREADS = 352;  // warp 0 TMA, warp 1 X/Y MMAs, warps 2..9 math (two threads per row), warp 10 accumulation MMAs
+constexpr int ATB2_CSTAGES = 6, ATB2_RSTAGES = 2, ATB2_NB = 3;
+
+template <bool DKV>
+__global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                    const __grid_constant__ CUtensorMap tmap_do,
+                                                                    const __grid_constant__ CUtensorMap tmap_qkv64,
+                                                                    const __grid_constant__ CUtensorMap tmap_do64,
+                                                                    const AttnBwdDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // smem: row operands R1 | R2 x 2 stages, column tiles (C1 | C2) x 4 stages, barriers, per-warp statistic rows
+  auto sR = [&](int st) { return smem_base + st * 2 * ATB_RTILE; };
+  auto sC = [&](int st) { return smem_base + ATB2_RSTAGES * 2 * ATB_RTILE + st * 2 * ATB_CTILE; };
+  const uint32_t misc_off = ATB2_RSTAGES * 2 * ATB_RTILE + ATB2_CSTAGES * 2 * ATB_CTILE;
+  const uint32_t bar_base = smem_base + misc_off;
+  auto r_full = [&](int s_) { return bar_base + 8u * s_; };
+  auto r_empty = [&](int s_) { return bar_base + 8u * (2 + s_); };
+  auto c_full = [&](int s_) { return bar_base + 8u * (4 + s_); };
+  auto c_empty = [&](int s_) { return bar_base + 8u * (10 + s_); };
+  auto bar_xy = [&](int b_) { return bar_base + 8u * (16 + b_); };     // X, Y of the tile in buffer b_ complete
+  auto bar_pd = [&](int b_) { return bar_base + 8u * (19 + b_); };     // P, dS written back
+  auto buf_free = [&](int b_) { return bar_base + 8u * (22 + b_); };   // accumulations have consumed P, dS
+  const uint32_t bar_acc = bar_base + 8u * 25, acc_empty = bar_base + 8u * 26;
+  const uint32_t tmem_slot = bar_base + 8u * 27;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 27);
+  float* s_stat = reinterpret_cast<float*>(smem_gen + misc_off + 256);  // [8 warps][lse * log2e 64 | D 64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = (int)((long long)p.total_items * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)p.total_items * (blockIdx.x + 1) / gridDim.x);
+  const int nrb = p.rblocks, ncb = p.cblocks;
+  const int n_tiles = (t1 - t0) * ncb;
+  constexpr uint32_t COL_A1 = 384, COL_A2 = 448;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_qkv64);
+    tma_prefetch_desc(&tmap_do64);
+    for (int i = 0; i < 16; ++i) mbar_init(bar_base + 8u * i, 1);
+    for (int b_ = 0; b_ < ATB2_NB; ++b_) {
+      mbar_init(bar_xy(b_), 1);
+      mbar_init(bar_pd(b_), 8);  // one arrival per math warp
+      mbar_init(buf_free(b_), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_sync();  // PDL: prologue overlapped the previous kernel; its results are visible from here on
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int cs = 0, n = 0;
+      uint32_t cph = 0;
+      for (int t = t0, itx = 0; t < t1; ++t, ++itx) {
+        const int bh = t / nrb, ob = t - bh * nrb;  // outer block: 128 keys (DKV) or 128 queries
+        const int b = bh / p.heads, h = bh - b * p.heads;
+        const int row0 = b * p.n_tok;
+        const int rs = itx & 1;
+        mbar_wait(r_empty(rs), ((itx >> 1) & 1) ^ 1);
+        mbar_expect_tx(r_full(rs), 2 * ATB_RTILE);
+        if (DKV) {
+          tma_load_2d(sR(rs), &tmap_qkv, r_full(rs), p.dim + h * 64, row0 + ob * 128);                  // K_j
+          tma_load_2d(sR(rs) + ATB_RTILE, &tmap_qkv, r_full(rs), 2 * p.dim + h * 64, row0 + ob * 128);  // V_j
+        } else {
+          tma_load_2d(sR(rs), &tmap_qkv, r_full(rs), h * 64, row0 + ob * 128);                          // Q_i
+          tma_load_2d(sR(rs) + ATB_RTILE, &tmap_do, r_full(rs), h * 64, row0 + ob * 128);               // dO_i
+        }
+        for (int ib = 0; ib < ncb; ++ib, ++n) {
+          mbar_wait(c_empty(cs), cph ^ 1);
+          mbar_expect_tx(c_full(cs), 2 * ATB_CTILE);
+          const uint32_t c1 = sC(cs), c2 = c1 + ATB_CTILE;
+          if (DKV) {
+            tma_load_2d(c1, &tmap_qkv64, c_full(cs), h * 64, row0 + ib * 64);            // Q (64 queries)
+            tma_load_2d(c2, &tmap_do64, c_full(cs), h * 64, row0 + ib * 64);             // dO
+          } else {
+            tma_load_2d(c1, &tmap_qkv64, c_full(cs), p.dim + h * 64, row0 + ib * 64);      // K (64 keys)
+            tma_load_2d(c2, &tmap_qkv64, c_full(cs), 2 * p.dim + h * 64, row0 + ib * 64);  // V
+          }
+          if (++cs == ATB2_CSTAGES) { cs = 0; cph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer 1: X = R1 C1^T, Y = R2 C2^T of tile m into buffer m % 3 =====================
+      const uint32_t idesc_xy = umma_idesc_bf16(128, 64);
+      long long pm[2] = {0, 0};  // waiting (operands, buffer) | issuing
+      const long long pm_t0 = kAtbProf ? clock64() : 0;
+      long long pt = pm_t0;
+      auto lap = [&](int i) { if (kAtbProf) { const long long c_ = clock64(); pm[i] += c_ - pt; pt = c_; } };
+      int x_item = 0, x_ib = 0, bi = 0, cs = 0;
+      uint32_t bph = 0, cph = 0;  // phase of this buffer's / stage's current use
+      for (int m = 0; m < n_tiles; ++m) {
+        const int rs = x_item & 1;
+        if (m >= ATB2_NB) mbar_wait(buf_free(bi), bph ^ 1);  // accumulations of tile m - 3 have consumed this buffer's P, dS
+        if (x_ib == 0) mbar_wait(r_full(rs), (x_item >> 1) & 1);
+        mbar_wait(c_full(cs), cph);
+        lap(0);
+        tc_fence_after();
+        const uint64_t dr1 = umma_desc_sw128(sR(rs)), dr2 = umma_desc_sw128(sR(rs) + ATB_RTILE);
+        const uint64_t dc1 = umma_desc_sw128(sC(cs)), dc2 = umma_desc_sw128(sC(cs) + ATB_CTILE);
+        const uint32_t tx = tmem_base + bi * 128, ty = tx + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tx, dr1 + 2 * k, dc1 + 2 * k, idesc_xy, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(ty, dr2 + 2 * k, dc2 + 2 * k, idesc_xy, k != 0);
+        umma_commit(bar_xy(bi));
+        if (x_ib == ncb - 1) umma_commit(r_empty(rs));  // row operands of this item no longer needed
+        if (++x_ib == ncb) { x_ib = 0; ++x_item; }
+        if (++bi == ATB2_NB) { bi = 0; bph ^= 1; }
+        if (++cs == ATB2_CSTAGES) { cs = 0; cph ^= 1; }
+        lap(1);
+      }
+      if (kAtbProf && p.prof) {
+        long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));
+        q[8] = pm[0]; q[9] = pm[1]; q[12] = clock64() - pm_t0;
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ===================== MMA issuer 2: acc1 += P C2 (dK/dV kernel), acc2 += dS C1 =====================
+      const uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
+      long long pm[2] = {0, 0};  // waiting for P, dS | issuing
+      long long pt = kAtbProf ? clock64() : 0;
+      auto lap = [&](int i) { if (kAtbProf) { const long long c_ = clock64(); pm[i] += c_ - pt; pt = c_; } };
+      int a_ib = 0, bi = 0, cs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int m = 0; m < n_tiles; ++m) {
+        mbar_wait(bar_pd(bi), bph);
+        if (a_ib == 0) mbar_wait(acc_empty, aph ^ 1);  // previous item's accumulators drained
+        lap(0);
+        tc_fence_after();
+        const uint64_t dm1 = umma_desc_sw128(sC(cs), 1024, 1024), dm2 = umma_desc_sw128(sC(cs) + ATB_CTILE, 1024, 1024);  // MN-major
+        const uint32_t tx = tmem_base + bi * 128, ty = tx + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile; 16 reduction rows = 2 KB per step
+          // P / dS of column half h sit packed in the first 16 TMEM columns of that half's own 32-column range
+          const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
+          if (DKV) umma_bf16_ts(tmem_base + COL_A1, tx + acol, dm2 + (2048 >> 4) * k, idesc_acc, (a_ib | k) != 0);
+          umma_bf16_ts(tmem_base + COL_A2, ty + acol, dm1 + (2048 >> 4) * k, idesc_acc, (a_ib | k) != 0);
+        }
+        umma_commit(c_empty(cs));
+        umma_commit(buf_free(bi));
+        if (a_ib == ncb - 1) umma_commit(bar_acc);
+        if (++a_ib == ncb) { a_ib = 0; aph ^= 1; }
+        if (++bi == ATB2_NB) { bi = 0; bph ^= 1; }
+        if (++cs == ATB2_CSTAGES) cs = 0;
+        lap(1);
+      }
+      if (kAtbProf && p.prof) {
+        long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));
+        q[10] = pm[0]; q[11] = pm[1];
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== softmax-backward math + epilogue (8 warps, two threads per row) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;   // which 32 of the 64 tile columns (and of the 64 accumulator columns) this thread owns
+    const int r = quad * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int n_tok = p.n_tok;
+    uint32_t aph = 0, bph = 0;
+    int bi = 0;  // TMEM buffer of the current tile (tile counter % 3) and the phase of its current use
+    long long pa[6] = {0, 0, 0, 0, 0, 0};  // statistics staging | wait X, Y | ld + math | st + arrive | item epilogue
+    const long long pa_t0 = kAtbProf ? clock64() : 0;
+    long long pt = pa_t0;
+    auto lap = [&](int i) { if (kAtbProf) { const long long c_ = clock64(); pa[i] += c_ - pt; pt = c_; } };
+    float* my_stat = s_stat + (warp - 2) * 128;
+    for (int t = t0; t < t1; ++t) {
+      const int bh = t / nrb, ob = t - bh * nrb;
+      const int b = bh / p.heads, h = bh - b * p.heads;
+      const long long vec0 = (long long)bh * n_tok;
+      const int orow = ob * 128 + r;  // key (DKV) or query index of this thread's row
+      float lse_r = 0.f, dsum_r = 0.f;
+      if (!DKV && orow < n_tok) {
+        lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
+        dsum_r = p.dsum[vec0 + orow];
+      }
+      auto load_stat = [&](int ib, float (&v)[4]) {  // raw loads, consumed one tile later (see version 1)
+        const int q0 = min(ib * 64 + lane, n_tok - 1), q1 = min(ib * 64 + 32 + lane, n_tok - 1);
+        v[0] = __ldg(p.lse + vec0 + q0);
+        v[1] = __ldg(p.lse + vec0 + q1);
+        v[2] = __ldg(p.dsum + vec0 + q0);
+        v[3] = __ldg(p.dsum + vec0 + q1);
+      };
+      float stat_next[4] = {0.f, 0.f, 0.f, 0.f};
+      if (DKV) load_stat(0, stat_next);
+      for (int ib = 0; ib < ncb; ++ib) {
+        const float* sl = my_stat;
+        const float* sd = my_stat + 64;
+        if (DKV) {
+          __syncwarp();
+          my_stat[lane] = stat_next[0] * 1.4426950408889634f; my_stat[32 + lane] = stat_next[1] * 1.4426950408889634f;
+          my_stat[64 + lane] = stat_next[2]; my_stat[96 + lane] = stat_next[3];
+          __syncwarp();
+          if (ib + 1 < ncb) load_stat(ib + 1, stat_next);
+        }
+        lap(0);
+        mbar_wait(bar_xy(bi), bph);
+        lap(1);
+        tc_fence_after();
+        const uint32_t tx = trow + bi * 128 + half * 32, ty = tx + 64;
+        uint32_t x[32], y[32], pp[16], pd[16];
+        tmem_ld32(tx, x);
+        tmem_ld32(ty, y);
+        tmem_ld_wait();
+        const bool interior = (ob * 128 + 127 < n_tok) && (ib * 64 + 63 < n_tok);  // CTA-uniform
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = half * 32 + 2 * j + e;
+              const float l2 = DKV ? sl[col] : lse_r;
+              const float dd = DKV ? sd[col] : dsum_r;
+              const float pr = ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2);
+              pv[e] = pr;
+              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
+            }
+            pp[j] = pack_bf16x2(pv[0], pv[1]);
+            pd[j] = pack_bf16x2(dv[0], dv[1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = half * 32 + 2 * j + e;
+              const int icol = ib * 64 + col;
+              const bool ok = orow < n_tok && icol < n_tok;
+              const float l2 = DKV ? sl[col] : lse_r;
+              const float dd = DKV ? sd[col] : dsum_r;
+              const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
+              pv[e] = pr;
+              dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
+            }
+            pp[j] = pack_bf16x2(pv[0], pv[1]);
+            pd[j] = pack_bf16x2(dv[0], dv[1]);
+          }
+        }
+        lap(2);
+        if (DKV) tmem_st16(tx, pp);
+        tmem_st16(ty, pd);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pd(bi));
+        if (++bi == ATB2_NB) { bi = 0; bph ^= 1; }
+        lap(3);
+      }
+      // ---- epilogue: accumulators -> bf16 rows of dqkv
+      mbar_wait(bar_acc, aph);
+      tc_fence_after();
+      uint32_t a0[32], b0[32];
+      tmem_ld32(trow + COL_A2 + half * 32, a0);
+      if (DKV) tmem_ld32(trow + COL_A1 + half * 32, b0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      {
+        // four neighbouring lanes write one row's 64 bytes (8 rows per store instruction, not 32 rows of 16 bytes)
+        const int row4 = ob * 128 + quad * 32 + (lane & ~3);  // first of this lane group's four rows
+        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + row4) * p.lddqkv + h * 64 + half * 32 + (lane & 3) * 8;
+        auto store32 = [&](__nv_bfloat16* dst, const uint32_t* v, float mul) {
+          uint4 c[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            c[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
+            c[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
+            c[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
+            c[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
+          }
+          lane4_transpose_u4(c, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (row4 + j < n_tok) *reinterpret_cast<uint4*>(dst + (long long)j * p.lddqkv) = c[j];
+        };
+        if (DKV) {
+          store32(base + p.dim, a0, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
+          store32(base + 2 * p.dim, b0, 1.f);  // dV = P^T dO                        (acc1)
+        } else {
+          store32(base, a0, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
+        }
+      }
+      aph ^= 1;
+      lap(4);
+    }
+    if (kAtbProf && p.prof && warp == 2 && lane == 0) {
+      long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));
+      for (int i = 0; i < 5; ++i) q[i] = pa[i];
+      q[5] = clock64() - pa_t0;
+      q[6] = n_tiles;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // D[b, h, q] = sum_d dO[q, h*64 + d] * O[q, h*64 + d]; one warp per (token row, 2 heads per pass)
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo,
                                      const __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ dsum,
@@ -434,6 +765,26 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   const CUtensorMap* tq64 = get_tmap_2d_bf16(qkv, rows, 3ull * p.dim, ldqkv, 64);
   const CUtensorMap* td64 = get_tmap_2d_bf16(dout, rows, (uint64_t)p.dim, lddo, 64);
   if (!tq || !td || !tq64 || !td64) return MV_ERR_ARG;
+  static const int ver_env = [] { const char* e = getenv("MV_ATTN_BWD_V"); return e ? atoi(e) : 2; }();  // 1: two CTAs per SM
+  if (ver_env != 1) {
+    const int smem2 = ATB2_RSTAGES * 2 * ATB_RTILE + ATB2_CSTAGES * 2 * ATB_CTILE + 256 + 8 * 128 * 4 + 1024;  // 166 KB
+    static std::atomic<uint64_t> attr2{0};  // one bit per device
+    if (first_use_on_device(attr2)) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(attn_bwd2): %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+    }
+    int grid2 = device_sms() > 0 ? device_sms() : 148;
+    if (grid2 > p.total_items) grid2 = p.total_items;
+    MV_LAUNCH((attn_bwd2_kernel<true>), grid2, ATB2_THREADS, smem2, stream, *tq, *td, *tq64, *td64, p);
+    MV_CHECK_LAUNCH("attn_bwd_dkv");
+    MV_LAUNCH((attn_bwd2_kernel<false>), grid2, ATB2_THREADS, smem2, stream, *tq, *td, *tq64, *td64, p);
+    MV_CHECK_LAUNCH("attn_bwd_dq");
+    return MV_OK;
+  }
   const int smem = 2 * ATB_RTILE + 4 * ATB_CTILE + 128 + 8 * 128 * 4 + 1024;
   static std::atomic<uint64_t> attr{0};  // one bit per device
   if (first_use_on_device(attr)) {

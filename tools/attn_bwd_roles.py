@@ -18,7 +18,7 @@ out, lse = ops.attn_fwd(qkv, B, N, H, want_lse=True)
 dq = ops.attn_bwd(qkv, out, do, lse, B, N, H)
 dsum = torch.empty((B, H, N), dtype=torch.float32, device="cuda")
 L = lib.init(0)
-G = 296
+G = 296 if os.environ.get("MV_ATTN_BWD_V") == "1" else 148  # CTAs per kernel (version 1: two per SM)
 buf = torch.zeros(16 * 2 * G, dtype=torch.int64, device="cuda")
 for _ in range(200):  # also brings the SM clock up
     ops.attn_bwd(qkv, out, do, lse, B, N, H, dqkv=dq, dsum=dsum)
