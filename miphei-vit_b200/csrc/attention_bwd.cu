@@ -379,7 +379,11 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
 // pair a single issuer was the bound (first cut of this version: 241 us against 215 us for version 1 at B = 32), so the X, Y
 // products and the accumulations have a thread each; "buffer free" travels between them as a commit barrier.
 //   TMEM: X0 0 | Y0 64 | X1 128 | Y1 192 | X2 256 | Y2 320 | acc1 384 | acc2 448   (tile n uses buffer n % 3; P / dS alias X / Y)
-constexpr int ATB2_THREADS = 352;  // warp 0 TMA, warp 1 X/Y MMAs, warps 2..9 math (two threads per row), warp 10 accumulation MMAs
+// With the MMAs off the critical path the eight math warps were the bound (two per scheduler, latency-bound: 46-53 % of a
+// tile pair in "ld + math"), so the math runs on SIXTEEN warps, four threads per row with 16 of the 64 tile columns each;
+// the first eight of them also write the item's accumulators out.
+constexpr int ATB2_THREADS = 608;  // warp 0 TMA, warp 1 X/Y MMAs, warps 2..17 math (four threads per row), warp 18 accumulation MMAs
+constexpr int ATB2_ACC_WARP = 18;
 constexpr int ATB2_CSTAGES = 6, ATB2_RSTAGES = 2, ATB2_NB = 3;
 
 template <bool DKV>
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
   const uint32_t bar_acc = bar_base + 8u * 25, acc_empty = bar_base + 8u * 26;
   const uint32_t tmem_slot = bar_base + 8u * 27;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + misc_off + 8 * 27);
-  float* s_stat = reinterpret_cast<float*>(smem_gen + misc_off + 256);  // [8 warps][lse * log2e 64 | D 64]
+  float* s_stat = reinterpret_cast<float*>(smem_gen + misc_off + 256);  // [16 warps][lse * log2e 16 | D 16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = (int)((long long)p.total_items * blockIdx.x / gridDim.x);
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
     for (int i = 0; i < 16; ++i) mbar_init(bar_base + 8u * i, 1);
     for (int b_ = 0; b_ < ATB2_NB; ++b_) {
       mbar_init(bar_xy(b_), 1);
-      mbar_init(bar_pd(b_), 8);  // one arrival per math warp
+      mbar_init(bar_pd(b_), 16);  // one arrival per math warp
       mbar_init(buf_free(b_), 1);
     }
     mbar_init(bar_acc, 1);
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         q[8] = pm[0]; q[9] = pm[1]; q[12] = clock64() - pm_t0;
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == ATB2_ACC_WARP) {
     if (lane == 0) {
       // ===================== MMA issuer 2: acc1 += P C2 (dK/dV kernel), acc2 += dS C1 =====================
       const uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
@@ -528,8 +532,8 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         const uint32_t tx = tmem_base + bi * 128, ty = tx + 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // K = 64 columns of this inner tile; 16 reduction rows = 2 KB per step
-          // P / dS of column half h sit packed in the first 16 TMEM columns of that half's own 32-column range
-          const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
+          // P / dS of column quarter k (one math thread's 16 columns) sit packed in the first 8 TMEM columns of that quarter
+          const uint32_t acol = k * 16;
           if (DKV) umma_bf16_ts(tmem_base + COL_A1, tx + acol, dm2 + (2048 >> 4) * k, idesc_acc, (a_ib | k) != 0);
           umma_bf16_ts(tmem_base + COL_A2, ty + acol, dm1 + (2048 >> 4) * k, idesc_acc, (a_ib | k) != 0);
         }
@@ -546,10 +550,11 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         q[10] = pm[0]; q[11] = pm[1];
       }
     }
-  } else if (warp < 10) {
-    // ===================== softmax-backward math + epilogue (8 warps, two threads per row) =====================
+  } else if (warp < ATB2_ACC_WARP) {
+    // ===================== softmax-backward math (16 warps, four threads per row) + epilogue (the first 8) =====================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;   // which 32 of the 64 tile columns (and of the 64 accumulator columns) this thread owns
+    const int cq = (warp - 2) >> 2;     // which 16 of the 64 tile columns this thread owns
+    const int half = cq;                // epilogue (cq < 2): which 32 of the 64 accumulator columns
     const int r = quad * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n_tok = p.n_tok;
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
     const long long pa_t0 = kAtbProf ? clock64() : 0;
     long long pt = pa_t0;
     auto lap = [&](int i) { if (kAtbProf) { const long long c_ = clock64(); pa[i] += c_ - pt; pt = c_; } };
-    float* my_stat = s_stat + (warp - 2) * 128;
+    float* my_stat = s_stat + (warp - 2) * 32;
     for (int t = t0; t < t1; ++t) {
       const int bh = t / nrb, ob = t - bh * nrb;
       const int b = bh / p.heads, h = bh - b * p.heads;
@@ -570,44 +575,43 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         lse_r = p.lse[vec0 + orow] * 1.4426950408889634f;
         dsum_r = p.dsum[vec0 + orow];
       }
-      auto load_stat = [&](int ib, float (&v)[4]) {  // raw loads, consumed one tile later (see version 1)
-        const int q0 = min(ib * 64 + lane, n_tok - 1), q1 = min(ib * 64 + 32 + lane, n_tok - 1);
-        v[0] = __ldg(p.lse + vec0 + q0);
-        v[1] = __ldg(p.lse + vec0 + q1);
-        v[2] = __ldg(p.dsum + vec0 + q0);
-        v[3] = __ldg(p.dsum + vec0 + q1);
+      // DKV: the statistics of this warp's 16 query columns of an inner tile (lanes 0..15 lse, lanes 16..31 D), fetched ONE
+      // TILE AHEAD as a raw load — nothing consumes the value before the next tile, so the warp never stalls on it
+      auto load_stat = [&](int ib) {
+        const int q = min(ib * 64 + cq * 16 + (lane & 15), n_tok - 1);
+        return __ldg((lane < 16 ? p.lse : p.dsum) + vec0 + q);
       };
-      float stat_next[4] = {0.f, 0.f, 0.f, 0.f};
-      if (DKV) load_stat(0, stat_next);
+      float stat_next = 0.f;
+      if (DKV) stat_next = load_stat(0);
       for (int ib = 0; ib < ncb; ++ib) {
         const float* sl = my_stat;
-        const float* sd = my_stat + 64;
+        const float* sd = my_stat + 16;
         if (DKV) {
           __syncwarp();
-          my_stat[lane] = stat_next[0] * 1.4426950408889634f; my_stat[32 + lane] = stat_next[1] * 1.4426950408889634f;
-          my_stat[64 + lane] = stat_next[2]; my_stat[96 + lane] = stat_next[3];
+          my_stat[lane] = lane < 16 ? stat_next * 1.4426950408889634f : stat_next;
           __syncwarp();
-          if (ib + 1 < ncb) load_stat(ib + 1, stat_next);
+          if (ib + 1 < ncb) stat_next = load_stat(ib + 1);
         }
         lap(0);
         mbar_wait(bar_xy(bi), bph);
         lap(1);
         tc_fence_after();
-        const uint32_t tx = trow + bi * 128 + half * 32, ty = tx + 64;
-        uint32_t x[32], y[32], pp[16], pd[16];
-        tmem_ld32(tx, x);
-        tmem_ld32(ty, y);
+        const uint32_t tx = trow + bi * 128 + cq * 16, ty = tx + 64;
+        uint32_t x[16], y[16], pp[8], pd[8];
+        tmem_ld16(tx, x);
+        tmem_ld16(ty, y);
         tmem_ld_wait();
+        // dS is formed WITHOUT the softmax scale (applied once per item to the accumulator in the epilogue), and tiles
+        // that lie completely inside the sequence skip the per-element bounds predicates
         const bool interior = (ob * 128 + 127 < n_tok) && (ib * 64 + 63 < n_tok);  // CTA-uniform
         if (interior) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             float pv[2], dv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = half * 32 + 2 * j + e;
-              const float l2 = DKV ? sl[col] : lse_r;
-              const float dd = DKV ? sd[col] : dsum_r;
+              const float l2 = DKV ? sl[2 * j + e] : lse_r;
+              const float dd = DKV ? sd[2 * j + e] : dsum_r;
               const float pr = ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2);
               pv[e] = pr;
               dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
@@ -617,15 +621,14 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             float pv[2], dv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = half * 32 + 2 * j + e;
-              const int icol = ib * 64 + col;
+              const int icol = ib * 64 + cq * 16 + 2 * j + e;
               const bool ok = orow < n_tok && icol < n_tok;
-              const float l2 = DKV ? sl[col] : lse_r;
-              const float dd = DKV ? sd[col] : dsum_r;
+              const float l2 = DKV ? sl[2 * j + e] : lse_r;
+              const float dd = DKV ? sd[2 * j + e] : dsum_r;
               const float pr = ok ? ex2a(__uint_as_float(x[2 * j + e]) * p.scale_log2e - l2) : 0.f;
               pv[e] = pr;
               dv[e] = pr * (__uint_as_float(y[2 * j + e]) - dd);
@@ -635,8 +638,8 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
           }
         }
         lap(2);
-        if (DKV) tmem_st16(tx, pp);
-        tmem_st16(ty, pd);
+        if (DKV) tmem_st8(tx, pp);
+        tmem_st8(ty, pd);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -644,6 +647,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         if (++bi == ATB2_NB) { bi = 0; bph ^= 1; }
         lap(3);
       }
+      if (cq >= 2) continue;  // the item's accumulators are written out by the first eight math warps
       // ---- epilogue: accumulators -> bf16 rows of dqkv
       mbar_wait(bar_acc, aph);
       tc_fence_after();
@@ -767,7 +771,7 @@ extern "C" int mv_attn_bwd(const void* qkv, int64_t ldqkv, const void* out, int6
   if (!tq || !td || !tq64 || !td64) return MV_ERR_ARG;
   static const int ver_env = [] { const char* e = getenv("MV_ATTN_BWD_V"); return e ? atoi(e) : 2; }();  // 1: two CTAs per SM
   if (ver_env != 1) {
-    const int smem2 = ATB2_RSTAGES * 2 * ATB_RTILE + ATB2_CSTAGES * 2 * ATB_CTILE + 256 + 8 * 128 * 4 + 1024;  // 166 KB
+    const int smem2 = ATB2_RSTAGES * 2 * ATB_RTILE + ATB2_CSTAGES * 2 * ATB_CTILE + 256 + 16 * 32 * 4 + 1024;  // 164 KB
     static std::atomic<uint64_t> attr2{0};  // one bit per device
     if (first_use_on_device(attr2)) {
       cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
