@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 2) attn_bwd_kernel(const __grid_c
 // products and the accumulations have a thread each; "buffer free" travels between them as a commit barrier.
 //   TMEM: X0 0 | Y0 64 | X1 128 | Y1 192 | X2 256 | Y2 320 | acc1 384 | acc2 448   (tile n uses buffer n % 3; P / dS alias X / Y)
 // With the MMAs off the critical path the eight math warps were the bound (two per scheduler, latency-bound: 46-53 % of a
-// tile pair in "ld + math"), so the math runs on SIXTEEN warps, four threads per row with 16 of the 64 tile columns each;
-// the first eight of them also write the item's accumulators out.
+// tile pair in "ld + math"), so the math runs on SIXTEEN warps, four threads per row with 16 of the 64 tile columns each.
+// An item's accumulators are written out AFTER the math of the next item's first tile: by then the last accumulation has
+// completed, so nobody waits for it (the epilogue was 20-27 % of a math warp's life when it followed the last tile directly).
 constexpr int ATB2_THREADS = 608;  // warp 0 TMA, warp 1 X/Y MMAs, warps 2..17 math (four threads per row), warp 18 accumulation MMAs
 constexpr int ATB2_ACC_WARP = 18;
 constexpr int ATB2_CSTAGES = 6, ATB2_RSTAGES = 2, ATB2_NB = 3;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
       mbar_init(buf_free(b_), 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(acc_empty, 8);
+    mbar_init(acc_empty, 16);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -553,8 +554,7 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
   } else if (warp < ATB2_ACC_WARP) {
     // ===================== softmax-backward math (16 warps, four threads per row) + epilogue (the first 8) =====================
     const int quad = warp & 3;
-    const int cq = (warp - 2) >> 2;     // which 16 of the 64 tile columns this thread owns
-    const int half = cq;                // epilogue (cq < 2): which 32 of the 64 accumulator columns
+    const int cq = (warp - 2) >> 2;     // which 16 of the 64 tile / accumulator columns this thread owns
     const int r = quad * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n_tok = p.n_tok;
@@ -565,6 +565,45 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
     long long pt = pa_t0;
     auto lap = [&](int i) { if (kAtbProf) { const long long c_ = clock64(); pa[i] += c_ - pt; pt = c_; } };
     float* my_stat = s_stat + (warp - 2) * 32;
+    // ---- an item's accumulators -> bf16 rows of dqkv (this thread: its row's 16 columns; two neighbouring lanes store one
+    // row's 32 bytes)
+    auto write_item = [&](int b, int h, int ob) {
+      mbar_wait(bar_acc, aph);
+      tc_fence_after();
+      uint32_t a0[16], b0[16];
+      tmem_ld16(trow + COL_A2 + cq * 16, a0);
+      if (DKV) tmem_ld16(trow + COL_A1 + cq * 16, b0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      const int row2 = ob * 128 + quad * 32 + (lane & ~1);  // first of this lane pair's two rows
+      __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + row2) * p.lddqkv + h * 64 + cq * 16 + (lane & 1) * 8;
+      auto store16 = [&](__nv_bfloat16* dst, const uint32_t* v_, float mul) {
+        uint4 c[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          c[j].x = pack_bf16x2(__uint_as_float(v_[8 * j + 0]) * mul, __uint_as_float(v_[8 * j + 1]) * mul);
+          c[j].y = pack_bf16x2(__uint_as_float(v_[8 * j + 2]) * mul, __uint_as_float(v_[8 * j + 3]) * mul);
+          c[j].z = pack_bf16x2(__uint_as_float(v_[8 * j + 4]) * mul, __uint_as_float(v_[8 * j + 5]) * mul);
+          c[j].w = pack_bf16x2(__uint_as_float(v_[8 * j + 6]) * mul, __uint_as_float(v_[8 * j + 7]) * mul);
+        }
+        lane2_transpose_u4(c, lane);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (row2 + j < n_tok) *reinterpret_cast<uint4*>(dst + (long long)j * p.lddqkv) = c[j];
+      };
+      if (DKV) {
+        store16(base + p.dim, a0, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
+        store16(base + 2 * p.dim, b0, 1.f);  // dV = P^T dO                        (acc1)
+      } else {
+        store16(base, a0, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
+      }
+      aph ^= 1;
+      lap(4);
+    };
+    bool pending = false;
+    int pend_b = 0, pend_h = 0, pend_ob = 0;
     for (int t = t0; t < t1; ++t) {
       const int bh = t / nrb, ob = t - bh * nrb;
       const int b = bh / p.heads, h = bh - b * p.heads;
@@ -646,46 +685,14 @@ __global__ void __launch_bounds__(ATB2_THREADS, 1) attn_bwd2_kernel(const __grid
         if (lane == 0) mbar_arrive(bar_pd(bi));
         if (++bi == ATB2_NB) { bi = 0; bph ^= 1; }
         lap(3);
-      }
-      if (cq >= 2) continue;  // the item's accumulators are written out by the first eight math warps
-      // ---- epilogue: accumulators -> bf16 rows of dqkv
-      mbar_wait(bar_acc, aph);
-      tc_fence_after();
-      uint32_t a0[32], b0[32];
-      tmem_ld32(trow + COL_A2 + half * 32, a0);
-      if (DKV) tmem_ld32(trow + COL_A1 + half * 32, b0);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      {
-        // four neighbouring lanes write one row's 64 bytes (8 rows per store instruction, not 32 rows of 16 bytes)
-        const int row4 = ob * 128 + quad * 32 + (lane & ~3);  // first of this lane group's four rows
-        __nv_bfloat16* base = p.dqkv + (long long)(b * n_tok + row4) * p.lddqkv + h * 64 + half * 32 + (lane & 3) * 8;
-        auto store32 = [&](__nv_bfloat16* dst, const uint32_t* v, float mul) {
-          uint4 c[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            c[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
-            c[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
-            c[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
-            c[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
-          }
-          lane4_transpose_u4(c, lane);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (row4 + j < n_tok) *reinterpret_cast<uint4*>(dst + (long long)j * p.lddqkv) = c[j];
-        };
-        if (DKV) {
-          store32(base + p.dim, a0, p.scale);  // dK = scale * (P .* (dP - D))^T Q   (acc2)
-          store32(base + 2 * p.dim, b0, 1.f);  // dV = P^T dO                        (acc1)
-        } else {
-          store32(base, a0, p.scale);          // dQ = scale * (P .* (dP - D)) K     (acc2)
+        if (ib == 0 && pending) {  // the previous item's accumulators: complete by now, and the accumulation thread is
+          write_item(pend_b, pend_h, pend_ob);  // holding this item's first accumulation until they have been read
+          pending = false;
         }
       }
-      aph ^= 1;
-      lap(4);
+      pend_b = b; pend_h = h; pend_ob = ob; pending = true;
     }
+    if (pending) write_item(pend_b, pend_h, pend_ob);
     if (kAtbProf && p.prof && warp == 2 && lane == 0) {
       long long* q = p.prof + 16ll * (blockIdx.x + (DKV ? 0 : gridDim.x));
       for (int i = 0; i < 5; ++i) q[i] = pa[i];

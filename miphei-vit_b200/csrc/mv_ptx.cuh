@@ -325,6 +325,18 @@ __device__ __forceinline__ void lane4_transpose_u4(uint4 (&a)[4], int lane) {
   xchg(a[1], a[3], 2);
 }
 
+// Two-lane version of lane4_transpose_u4: lane 2g+t holds the two 16-byte chunks of ITS row on entry and chunk t of rows
+// 2g, 2g+1 on exit (a[j] = chunk t of row 2g+j): two neighbouring lanes store one row's 32 bytes.
+__device__ __forceinline__ void lane2_transpose_u4(uint4 (&a)[2], int lane) {
+  const bool hi = (lane & 1) != 0;
+  uint4 send = hi ? a[0] : a[1], recv;
+  recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+  recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+  recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+  recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+  if (hi) a[0] = recv; else a[1] = recv;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
