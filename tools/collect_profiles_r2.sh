@@ -7,7 +7,7 @@
 #   4. in-pipeline per-op times (CUDA events around every ops.* call, all 40 blocks), attention / elementwise microbenches
 O=gpurun_out
 set -x
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline > $O/r02_bench_under_ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_bf16|attn_|layernorm|upsample|tokens_to_map|prep_|patch_|fill_prefix|heads_|bn_|gram32" -c 1200 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline > $O/r02_bench_under_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launches_infer_d4.csv python tools/profile_infer.py 16 4 > $O/pi.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launches_train_d4.csv python tools/profile_train.py 32 4 > $O/pt.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"gemm_bf16|attn_fwd|layernorm|upsample|tokens_to_map|prep_|patch_" --launch-skip 40 --launch-count 36 -o $O/r02_infer_full python tools/profile_infer.py 16 2 3 > $O/pf.log 2>&1
