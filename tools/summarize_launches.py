@@ -30,11 +30,12 @@ def main():
         elif r.get("Metric Unit") == "ms":
             t *= 1e3
         rows.append((r["Kernel Name"], r["Grid Size"], r["Block Size"], t))
-    start = 0
-    for i, r in enumerate(rows):
-        if marker in r[0]:
-            start = i
-    step = rows[start:]
+    marks = [i for i, r in enumerate(rows) if marker in r[0]]
+    start, end = (marks[-1] if marks else 0), len(rows)
+    # a launch-count limit (ncu -c N) may cut the last step short: then list the last COMPLETE one
+    if len(marks) >= 3 and end - marks[-1] < marks[-1] - marks[-2]:
+        start, end = marks[-2], marks[-1]
+    step = rows[start:end]
     tot = sum(r[3] for r in step)
     print("# step: %d launches, %.1f us total (cold-cache, serialised ncu times)" % (len(step), tot))
     agg = OrderedDict()
