@@ -21,7 +21,8 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 329, 3), (1, 86, 2), (2, 128, 1), (1, 384, 2), (3, 200, 2), (4, 329, 24)])
+@pytest.mark.parametrize("B,N,H", [(2, 329, 3), (1, 86, 2), (2, 128, 1), (1, 384, 2), (3, 200, 2), (4, 329, 24), (3, 16, 2), (2, 48, 1),
+                                   (8, 64, 24), (1, 1301, 2), (1, 700, 3), (40, 33, 24)])
 def test_attention_backward(B, N, H):
     ops = _ops()
     D = H * 64
