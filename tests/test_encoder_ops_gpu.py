@@ -16,7 +16,7 @@ def _rand(shape, scale=1.0, seed=0):
     return torch.randn(shape, generator=g, device="cuda") * scale
 
 
-@pytest.mark.parametrize("M,D", [(5264, 1536), (77, 128), (1000, 256), (329, 768)])
+@pytest.mark.parametrize("M,D", [(5264, 1536), (77, 128), (1000, 256), (329, 768), (10528, 1536), (2400, 1536), (9000, 256)])
 def test_layernorm_fwd_bwd(M, D):
     ops = _ops()
     x = _rand((M, D), 2.0, 1) + 0.5

@@ -31,6 +31,7 @@ x = torch.randn(10528, 1536, device="cuda")
 w = torch.ones(1536, device="cuda"); b_ = torch.zeros(1536, device="cuda")
 y = torch.empty(10528, 1536, device="cuda", dtype=bf)
 t("layernorm_fwd M=10528", lambda: ops.layernorm_fwd(x, w, b_, out=y), 10528 * 1536 * 6)
+t("layernorm_fwd M=5264", lambda: ops.layernorm_fwd(x[:5264], w, b_, out=y[:5264]), 5264 * 1536 * 6)
 dy = torch.randn(10528, 1536, device="cuda").to(bf); dres = torch.randn(10528, 1536, device="cuda")
 dx = torch.empty_like(x); dxb = torch.empty_like(y)
 t("layernorm_bwd M=10528", lambda: ops.layernorm_bwd(x, w, dy, dres=dres, out=dx, out_bf16=dxb), 10528 * 1536 * (4 + 2 + 4 + 4 + 2))
