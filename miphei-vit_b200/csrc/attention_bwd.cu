@@ -11,10 +11,12 @@
 //                operands, the kernel loops over 128-query tiles and accumulates dV, dK of the block in TMEM.
 //   DKV = false: work item = (image, head, 128-query tile); Q, dO are the row operands, the loop runs over key blocks and
 //                accumulates dQ.  (S and dP are recomputed by both instances: 7 MMAs per tile pair instead of 5.)
-// Per (128-row block, 64-column tile) pair: X = R1 C1^T and Y = R2 C2^T (SS MMAs) -> 4 warps (one row per thread) turn
-// X into P and Y into dS (bf16, written back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A
-// operand read from TMEM and the C tiles re-read from the SAME smem tiles as MN-major operands.  Two CTAs are resident per
-// SM (64 KB smem, 256 TMEM columns each), so one CTA's exponentials overlap the other CTA's MMAs.
+// Per (128-row block, 64-column tile) pair: X = R1 C1^T and Y = R2 C2^T (SS MMAs) -> the math warps turn X into P and Y
+// into dS (bf16, written back over X / Y in TMEM) -> acc1 += P C2 (DKV only) and acc2 += dS C1 with the A operand read
+// from TMEM and the C tiles re-read from the SAME smem tiles as MN-major operands.
+// Two schedules of this: attn_bwd_kernel (round 1, MV_ATTN_BWD_V=1) runs two CTAs per SM (64 KB smem, 256 TMEM columns
+// each) so that one CTA's exponentials overlap the other CTA's MMAs; attn_bwd2_kernel (default, further down) runs one CTA
+// per SM with X / Y triple-buffered, two MMA-issuing threads and sixteen math warps.
 #include <stdlib.h>
 
 #include "mv_host.h"
